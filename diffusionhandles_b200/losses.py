@@ -1,0 +1,186 @@
+"""Drop-in mirror of the reference's ``diffhandles/losses.py`` (same call signatures, 0-d fp32 results that are
+differentiable w.r.t. ``activations``) backed by the fused K4 kernel, plus the fused multi-layer entry point
+``guidance_loss`` that ``guided_inference`` (guided_stable_diffuser.py:417-434) evaluates every step.
+
+Each call is ONE kernel pass that produces the loss value AND the gradient (stashed for autograd's backward);
+backward only rescales the stash by the incoming gradient - and exits on the device when that is 1.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .guided_stable_diffuser import ProcessedCorrespondences
+
+_FG, _BG_GLOBAL, _BG_LOCAL = 1, 1, 2
+
+
+def _to_cells(y, x, grid: int, device) -> torch.Tensor:
+    yy = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y).to(device=device, dtype=torch.int64)
+    xx = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(device=device, dtype=torch.int64)
+    return (yy.reshape(-1) * grid + xx.reshape(-1)).to(torch.int32).contiguous()
+
+
+def _lists(pc, grid: int, device) -> Dict[str, torch.Tensor]:
+    """Device-side int32 cell lists for a processed-correspondences dict."""
+    if isinstance(pc, ProcessedCorrespondences) and pc.grid == grid and pc.device_lists["fg_src"].device == device:
+        return pc.device_lists
+    return {
+        "fg_src": _to_cells(pc['original_y'], pc['original_x'], grid, device),
+        "fg_dst": _to_cells(pc['transformed_y'], pc['transformed_x'], grid, device),
+        "bg": _to_cells(pc['background_y'], pc['background_x'], grid, device),
+        "bg_orig": _to_cells(pc['background_y_orig'], pc['background_x_orig'], grid, device),
+        "bg_trans": _to_cells(pc['background_y_trans'], pc['background_x_trans'], grid, device),
+    }
+
+
+def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_grad: Sequence[bool],
+            fgw: Sequence[float], bgw: Sequence[float], grid: int, fg_src, fg_dst, bg_orig, bg_trans, bg_common,
+            fg_kind: int, bg_kind: int) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+    lib = N.load()
+    dev = curs[0].device
+    if dev.type != "cuda":
+        raise N.NativeLibraryError("guidance losses run on CUDA only; there is no CPU fallback")
+    L = len(curs)
+    layers = (N.dh_loss_layer * L)()
+    grads: List[Optional[torch.Tensor]] = []
+    keep = []
+    for i, (c, o) in enumerate(zip(curs, origs)):
+        if c.dim() != 3 or tuple(c.shape) != tuple(o.shape):
+            raise ValueError("activations must be (C,h,w) with matching recorded activations")
+        c32 = c.detach().to(torch.float32).contiguous()
+        o32 = o.detach().to(device=dev, dtype=torch.float32).contiguous()
+        g = torch.empty_like(c32) if want_grad[i] else None
+        keep += [c32, o32]
+        grads.append(g)
+        layers[i].cur, layers[i].orig = N.ptr(c32), N.ptr(o32)
+        layers[i].grad = N.ptr(g) if g is not None else None
+        layers[i].channels, layers[i].h, layers[i].w = c32.shape
+        layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
+    total_c = sum(int(c.shape[0]) for c in curs)
+    ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(int(c.shape[0]) for c in curs)))
+    ws_bytes = max(ws_bytes, 8 * total_c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
+
+    def p(t):
+        return N.ptr(t, torch.int32) if t is not None and t.numel() else None
+
+    def n(t):
+        return int(t.numel()) if t is not None else 0
+    N.check(lib.dh_guidance_loss(layers, L, grid, p(fg_src), p(fg_dst), n(fg_src), p(bg_orig), n(bg_orig), p(bg_trans),
+                                 n(bg_trans), p(bg_common), n(bg_common), fg_kind, bg_kind, N.ptr(out), N.ptr(ws), ws_bytes,
+                                 N.stream_handle(dev)), "dh_guidance_loss")
+    return out, grads
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, *acts):
+        L = spec["L"]
+        curs, origs = acts[:L], acts[L:]
+        want = [ctx.needs_input_grad[1 + i] for i in range(L)]
+        out, grads = _launch(curs, origs, want, spec["fgw"], spec["bgw"], spec["grid"], spec.get("fg_src"), spec.get("fg_dst"),
+                             spec.get("bg_orig"), spec.get("bg_trans"), spec.get("bg_common"), spec["fg_kind"], spec["bg_kind"])
+        ctx.grads = grads
+        ctx.n_inputs = len(acts)
+        total, parts = out[0].clone(), out[1:].clone()
+        ctx.mark_non_differentiable(parts)
+        return total, parts
+
+    @staticmethod
+    def backward(ctx, g_total, _g_parts):
+        lib = N.load()
+        res = [None] * (1 + ctx.n_inputs)
+        for i, g in enumerate(ctx.grads):
+            if g is None:
+                continue
+            scale = g_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
+            N.check(lib.dh_scale_inplace(N.ptr(g), g.numel(), N.ptr(scale), N.stream_handle(g.device)), "dh_scale_inplace")
+            res[1 + i] = g
+        ctx.grads = None
+        return tuple(res)
+
+
+def _grid_of(activations_size) -> int:
+    hs, ws = int(activations_size[0]), int(activations_size[1])
+    if hs != ws:
+        raise NotImplementedError("only square loss grids are implemented (the reference always uses (64, 64))")
+    return hs
+
+
+def guidance_loss(activations: Sequence[torch.Tensor], activations_orig: Sequence[torch.Tensor], processed_correspondences,
+                  fg_weights: Sequence[float], bg_weights: Sequence[float], bg_loss_type: str = 'global_avg',
+                  activations_size=(64, 64), patch_size: int = 1):
+    """sum_l fgw[l]*compute_foreground_loss(l) + bgw[l]*compute_background_loss(l) in ONE fused launch
+    (guided_stable_diffuser.py:417-428).  Returns (total 0-d tensor, per-term values (2L,) tensor)."""
+    if patch_size != 1:
+        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    if bg_loss_type not in ('global_avg', 'local_avg'):
+        raise ValueError(f'Unknown background loss type: {bg_loss_type}')
+    grid = _grid_of(activations_size)
+    dev = activations[0].device
+    ls = _lists(processed_correspondences, grid, dev)
+    spec = dict(L=len(activations), fgw=list(fg_weights), bgw=list(bg_weights), grid=grid, fg_src=ls["fg_src"], fg_dst=ls["fg_dst"],
+                bg_orig=ls["bg_orig"], bg_trans=ls["bg_trans"], bg_common=ls["bg"], fg_kind=_FG,
+                bg_kind=_BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL)
+    return _FusedLoss.apply(spec, *activations, *activations_orig)
+
+
+def compute_foreground_loss(activations, activations_orig, processed_correspondences, patch_size, activations_size):
+    """losses.py:4-17."""
+    if patch_size != 1:
+        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    grid = _grid_of(activations_size)
+    ls = _lists(processed_correspondences, grid, activations.device)
+    spec = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=ls["fg_src"], fg_dst=ls["fg_dst"], fg_kind=_FG, bg_kind=0)
+    return _FusedLoss.apply(spec, activations, activations_orig)[0]
+
+
+def compute_background_loss(activations, activations_orig, processed_correspondences, patch_size, activations_size,
+                            loss_type='global_avg'):
+    """losses.py:19-40."""
+    if loss_type not in ('global_avg', 'local_avg'):
+        raise ValueError(f'Unknown background loss type: {loss_type}')
+    if loss_type == 'local_avg' and patch_size != 1:
+        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    grid = _grid_of(activations_size)
+    ls = _lists(processed_correspondences, grid, activations.device)
+    spec = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=ls["bg_orig"], bg_trans=ls["bg_trans"], bg_common=ls["bg"],
+                fg_kind=0, bg_kind=_BG_GLOBAL if loss_type == 'global_avg' else _BG_LOCAL)
+    return _FusedLoss.apply(spec, activations, activations_orig)[0]
+
+
+def _two_sided(spec_fwd, spec_swapped, feat_map_1, feat_map_2):
+    """Loss that is differentiable w.r.t. both maps: |a-b| is symmetric, so the gradient w.r.t. feat_map_1 is
+    the same kernel with the roles of the two maps (and of their index lists) swapped."""
+    loss = _FusedLoss.apply(spec_fwd, feat_map_2, feat_map_1.detach())[0]
+    if feat_map_1.requires_grad:
+        other = _FusedLoss.apply(spec_swapped, feat_map_1, feat_map_2.detach())[0]
+        loss = loss + (other - other.detach())      # value counted once, gradient flows to feat_map_1
+    return loss
+
+
+def average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2):
+    """losses.py:42-49: |mean_n f1[:,y1,x1] - mean_n f2[:,y2,x2]|.mean()."""
+    grid = _grid_of(feat_map_1.shape[-2:])
+    dev = feat_map_2.device
+    a, b = _to_cells(y1, x1, grid, dev), _to_cells(y2, x2, grid, dev)
+    fwd = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=a, bg_trans=b, fg_kind=0, bg_kind=_BG_GLOBAL)
+    swp = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=b, bg_trans=a, fg_kind=0, bg_kind=_BG_GLOBAL)
+    return _two_sided(fwd, swp, feat_map_1, feat_map_2)
+
+
+def local_average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2, patch_size=1):
+    """losses.py:51-84 with patch_size == 1: mean_c mean_n |f1[c,y1,x1] - f2[c,y2,x2]|."""
+    if patch_size != 1:
+        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    grid = _grid_of(feat_map_1.shape[-2:])
+    dev = feat_map_2.device
+    a, b = _to_cells(y1, x1, grid, dev), _to_cells(y2, x2, grid, dev)
+    fwd = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=a, fg_dst=b, fg_kind=_FG, bg_kind=0)
+    swp = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=b, fg_dst=a, fg_kind=_FG, bg_kind=0)
+    return _two_sided(fwd, swp, feat_map_1, feat_map_2)
