@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py - activation-stack warps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE config 2): per GPU, 256 independent edits, each with its own full SD2-depth
+activation stack (64^2x320, 32^2x640, 16^2x1280, 8^2x1280 fp32 = 9.5 MB) warped through that edit's winner-index
+map.  The 256 maps come from 256 real splats (16 synthetic depths x 16 rigid transforms, config 4 recipe).
+One *step* = one pass of K3 over the 256 stacks (2.43 GB read + 2.43 GB written, far larger than L2).
+
+  value     device-resident: stacks and maps already in HBM, one kernel launch per step, CUDA-event timed.
+  e2e       the same 256 edits through the public batched API with HOST (pinned) buffers: H2D of depth, mask and
+            stack, K1 -> K2 -> masks -> correspondences -> maps -> K3, D2H of the warped stack and counts.
+  roofline  algorithmic bytes (19,027,200 B per warp) / K3 launch time vs the measured HBM copy peak.
+  cpu_baseline  the oracle port of the reference path (NumPy geometry + torch CPU index gather) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+LEVELS = [(320, 64), (640, 32), (1280, 16), (1280, 8)]        # (channels, side) - BASELINE config 2
+S = 512
+EDITS_PER_GPU = 256
+STACK_FLOATS = sum(c * s * s for c, s in LEVELS)                 # 2,375,680
+ALGO_BYTES_PER_WARP = 2 * STACK_FLOATS * 4 + sum(s * s for _, s in LEVELS) * 4   # 19,027,200
+METRIC = "activation_stack_warps_per_sec"
+UNIT = "warps/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def edit_recipe(n_edits: int):
+    """Config-4 recipe: 16 synthetic depths (seeds 100..115, disc radius U[60,160], centre jitter +-60 px) x 16
+    transforms (angles linspace(-90,90,16) about (0,1,0); t = (0.1k-0.8, 0, 0.05k))."""
+    rng = np.random.default_rng(1234)
+    scenes = []
+    for i in range(16):
+        scenes.append(dict(S=S, seed=100 + i, cx=256.0 + float(rng.uniform(-60, 60)), cy=280.0 + float(rng.uniform(-60, 60)),
+                           radius=float(rng.uniform(60, 160))))
+    angles = np.linspace(-90.0, 90.0, 16)
+    edits = []
+    for e in range(n_edits):
+        si, k = (e // 16) % 16, e % 16
+        edits.append((si, float(angles[k]), (0.0, 1.0, 0.0), (0.1 * k - 0.8, 0.0, 0.05 * k)))
+    return scenes, edits
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference path)
+# ------------------------------------------------------------------------------------------------
+def cpu_warp_sample(n_stacks: int, with_geometry: bool, seed: int = 0):
+    """Times the oracle port on `n_stacks` edits of the bench workload.  Returns (gather warps/s, e2e warps/s)."""
+    from oracle import dh_oracle as O
+    scenes, edits = edit_recipe(n_stacks)
+    K = O.get_depth_intrinsics()
+    g = torch.Generator().manual_seed(seed)
+    t_geo = t_gather = 0.0
+    cache = {}
+    for (si, angle, axis, t) in edits:
+        if si not in cache:
+            cache[si] = O.synthetic_scene(**scenes[si])
+        depth, bg, mask = cache[si]
+        t0 = time.perf_counter()
+        o = O.transform_depth_pc(depth, bg, mask, K, angle, axis, tuple(float(np.float32(v)) for v in t), poisson=False)
+        P = S * S
+        ws = np.where(o["winner"] < 0, -1, np.where(o["winner"] < P, o["winner"], 0))
+        fgw = o["winner"] >= P
+        ws[fgw] = o["fg_index"][o["winner"][fgw] - P]
+        maps = [O.dense_source_map(o["correspondences"], S, s, ws) for _, s in LEVELS]
+        t_geo += time.perf_counter() - t0
+        stack = [torch.randn((c, s, s), generator=g) for c, s in LEVELS]
+        t0 = time.perf_counter()
+        for A, m in zip(stack, maps):
+            idx = torch.from_numpy(np.where(m >= 0, m, 0).astype(np.int64))
+            out = A.flatten(1)[:, idx]                       # the reference's gather: feat_map[..., y, x] (losses.py:46-47)
+            out[:, torch.from_numpy(m < 0)] = 0
+        t_gather += time.perf_counter() - t0
+    return n_stacks / t_gather, n_stacks / (t_gather + t_geo)
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    n = 4
+    for _ in range(args.warmup):
+        cpu_warp_sample(1, True)
+    t0 = time.perf_counter()
+    vals = [cpu_warp_sample(n, True) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    e2e = float(np.mean([v[1] for v in vals]))
+    sample = (f"per step: {n} edits of the bench workload (oracle NumPy port of transform_depth_pc + dense maps + torch CPU "
+              f"index gather of the 4-level stack), geometry included")
+    line = {"impl": "reference", "metric": METRIC, "value": e2e, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: full SD2-depth activation stack (64^2x320,32^2x640,16^2x1280,8^2x1280) per edit, "
+                                   "512^2 depth, config-4 edit recipe"},
+            "cpu_baseline": {"value": e2e, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_workload(dev, n_edits: int, full_map: bool):
+    """Runs the real geometry (K1 -> K2 -> masks -> correspondences) for n_edits edits and returns the per-level
+    source maps (device) plus host copies of the geometry inputs."""
+    from diffusionhandles_b200 import warp
+    from diffusionhandles_b200.synthetic import synthetic_scene
+    from diffusionhandles_b200.engine import EditEngine, make_rigid
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
+    scenes, edits = edit_recipe(n_edits)
+    K = GuidedStableDiffuser.get_depth_intrinsics()
+    chunk = 16
+    eng = EditEngine(dev, chunk, S, S)
+    sc = [synthetic_scene(**s) for s in scenes]
+    depth_h = torch.empty((n_edits, S, S), dtype=torch.float32).pin_memory()
+    bg_h = torch.empty((n_edits, S, S), dtype=torch.float32).pin_memory()
+    mask_h = torch.empty((n_edits, S, S), dtype=torch.float32).pin_memory()
+    rigids = []
+    for e, (si, angle, axis, t) in enumerate(edits):
+        depth_h[e] = torch.from_numpy(sc[si][0]); bg_h[e] = torch.from_numpy(sc[si][1]); mask_h[e] = torch.from_numpy(sc[si][2])
+        rigids.append(make_rigid(angle, list(axis), list(t)))
+    maps = [torch.empty((n_edits, s * s), dtype=torch.int32, device=dev) for _, s in LEVELS]
+    n_corr = torch.empty(n_edits, dtype=torch.int32, device=dev)
+    for e0 in range(0, n_edits, chunk):
+        e1 = e0 + chunk
+        res = eng.run(depth_h[e0:e1].to(dev), bg_h[e0:e1].to(dev), mask_h[e0:e1].to(dev), K, rigids[e0:e1], poisson=False)
+        ms = warp.dense_source_maps(res.corr, res.n_corr, S, [s for _, s in LEVELS], res.winner_src if full_map else None)
+        for dst, m in zip(maps, ms):
+            dst[e0:e1] = m
+        n_corr[e0:e1] = res.n_corr
+    torch.cuda.synchronize(dev)
+    del eng
+    return dict(depth_h=depth_h, bg_h=bg_h, mask_h=mask_h, rigids=rigids, K=K, maps=maps, n_corr=n_corr)
+
+
+def time_kernel_steps(fn, steps: int, warmup: int, dev):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from diffusionhandles_b200 import warp, _native
+    from diffusionhandles_b200.batch import EditWarpPipeline
+    rank, world, local = dist_env()
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _native.load()
+    n_edits = EDITS_PER_GPU
+    wl = build_workload(dev, n_edits, full_map=True)
+    gen = torch.Generator(device=dev).manual_seed(2 + rank)
+    levels = [torch.randn((n_edits, c, s, s), generator=gen, dtype=torch.float32, device=dev) for c, s in LEVELS]
+    outs = [torch.empty_like(l) for l in levels]
+    maps = wl["maps"]
+
+    def step():
+        warp.warp_stacks(levels, maps, outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident metric: K steps, barrier + sync on both sides, max over ranks ----
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n_edits * args.steps / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----
+    per_launch = time_kernel_steps(step, max(args.steps, 10), 3, dev)
+    k3_ms = float(np.mean(per_launch))
+    achieved = ALGO_BYTES_PER_WARP * n_edits / (k3_ms * 1e-3) / 1e9
+    peak, peak_kind = measured_peak_hbm()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile": True, "ms_per_launch": k3_ms, "achieved_gbs": achieved, "frac": achieved / peak}), flush=True)
+        return
+
+    # parity spot check inside the bench: the timed kernel really produced the gather (3 stacks, torch indexing)
+    for l, m, o in zip(levels, maps, outs):
+        for e in (0, n_edits // 2, n_edits - 1):
+            idx = m[e].long().clamp(min=0)
+            ref = l[e].flatten(1)[:, idx] * (m[e] >= 0)
+            assert torch.equal(o[e].flatten(1), ref), "K3 output differs from an index gather"
+
+    # ---- variant: correspondence-only maps (SURVEY.md row 9 dense form; ~80% of the cells are empty) ----
+    wl2 = build_workload(dev, n_edits, full_map=False)
+    maps2 = wl2["maps"]
+    outs2 = [torch.empty_like(l) for l in levels]
+    corr_only = time_kernel_steps(lambda: warp.warp_stacks(levels, maps2, outs2), 10, 3, dev)
+    coverage = float(np.mean([(m >= 0).float().mean().item() for m in maps]))
+    coverage2 = float(np.mean([(m >= 0).float().mean().item() for m in maps2]))
+    del wl2, maps2, outs2
+
+    # ---- end to end through the public batched API with pinned HOST buffers ----
+    e2e_steps = max(2, min(args.steps, 5))
+    pipe = EditWarpPipeline(dev, S, LEVELS, chunk=16, n_streams=3, full_winner_map=True)
+    levels_h = [torch.empty((n_edits, c, s, s), dtype=torch.float32).pin_memory() for c, s in LEVELS]
+    for h, d in zip(levels_h, levels):
+        h.copy_(d)
+    outs_h = [torch.empty((n_edits, c, s, s), dtype=torch.float32).pin_memory() for c, s in LEVELS]
+    n_corr_h = torch.empty(n_edits, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        pipe.run_host(wl["depth_h"], wl["bg_h"], wl["mask_h"], wl["K"], wl["rigids"], levels_h, outs_h, n_corr_h)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_edits * e2e_steps / float(te.item())
+    assert torch.equal(n_corr_h, wl["n_corr"].cpu()), "e2e correspondences differ from the device-resident run"
+    for h, o in zip(outs_h, outs):
+        assert torch.equal(h[-1], o[-1].cpu()), "e2e warped stack differs from the device-resident run"
+
+    # ---- one NCCL gather of small per-edit result records (not on the hot path) ----
+    gather_ms = None
+    if world > 1:
+        rec = torch.stack([wl["n_corr"].to(torch.int64), outs[0].flatten(1).sum(1).double().view(torch.int64)], dim=1).contiguous()
+        buf = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        dist.gather(rec, buf, dst=0)
+        torch.cuda.synchronize(dev)
+        gather_ms = 1e3 * (time.perf_counter() - t0)
+
+    line = None
+    if rank == 0:
+        n_cpu = 24
+        cpu_warp_sample(1, True)
+        cpu_gather, cpu_e2e = cpu_warp_sample(n_cpu, True)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: full SD2-depth activation stack (64^2x320,32^2x640,16^2x1280,8^2x1280) per edit, "
+                                   "256 edits per GPU, each through its own winner-index map (512^2 splat, config-4 edit recipe)",
+                       "edits_per_gpu": n_edits, "bytes_per_warp": ALGO_BYTES_PER_WARP, "map": "full winner-index map",
+                       "map_coverage": coverage, "l2": "inputs (2.43 GB read + 2.43 GB written per step) far larger than L2; no flush",
+                       "parallelism": f"{world} x independent shards, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                         "kernel": "warp_dense_tma_kernel", "ms_per_launch": k3_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WARP * n_edits},
+            "cpu_baseline": {"value": cpu_e2e, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{n_cpu} edits of the same workload: oracle NumPy port of transform_depth_pc + dense maps + "
+                                       f"torch CPU index gather of the 4-level stack (gather alone: {cpu_gather:.1f} warps/s)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_edit() * n_edits,
+                    "d2h_bytes_per_step": pipe.d2h_bytes_per_edit() * n_edits, "steps": e2e_steps,
+                    "what": "pinned host depth/mask/stack -> K1,K2,masks,correspondences,maps,K3 -> pinned host warped stack"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "variants": {"corr_only_map": {"ms_per_launch": float(np.mean(corr_only)), "map_coverage": coverage2,
+                                           "warps_per_s": n_edits / (float(np.mean(corr_only)) * 1e-3)}},
+            "wall_s_timed_region": wall, "result_gather_ms": gather_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="device-resident K3 steps only (for ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

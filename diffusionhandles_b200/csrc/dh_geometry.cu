@@ -165,42 +165,54 @@ __global__ void __launch_bounds__(kTileThreads) fg_compact_kernel(
 
 // Sequential fp32 sum in raster order, one warp per component (np.mean(points[mask], axis=0) adds row
 // by row, depth_transform.py:509).  All 32 lanes carry the same running sum; the addends are fetched
-// 32 at a time (coalesced) and broadcast with shuffles, so only the dependent FADD chain is serial.
+// 256 at a time (two coalesced float4 per lane, next tile prefetched while the current one is consumed)
+// and broadcast with shuffles, so only the dependent FADD chain (4 cycles per element) is serial.
 __global__ void __launch_bounds__(96) fg_centroid_kernel(const float* __restrict__ fgX, const float* __restrict__ fgY,
                                                          const float* __restrict__ fgZ, const int32_t* __restrict__ n_fg,
                                                          int P, float* __restrict__ centroid) {
     const int e = blockIdx.x, comp = warp_id(), lane = lane_id();
-    const float* a = (comp == 0 ? fgX : comp == 1 ? fgY : fgZ) + (size_t)e * P;
+    const float* a = (comp == 0 ? fgX : comp == 1 ? fgY : fgZ) + (size_t)e * P;   // 256-byte aligned (workspace layout)
     const int n = n_fg[e];
+    const unsigned full = 0xFFFFFFFFu;
     float s = 0.0f;
-    float next = lane < n ? a[lane] : 0.0f;
-    for (int base = 0; base < n; base += 32) {
-        const float v = next;
-        const int nb = base + 32 + lane;
-        next = nb < n ? a[nb] : 0.0f;
-        const int cnt = min(32, n - base);
-        if (cnt == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xFFFFFFFFu, v, j));
-        } else {
-            for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xFFFFFFFFu, v, j));
+    const int n_tiles = (reinterpret_cast<uintptr_t>(a) & 15) == 0 ? n / 256 : 0;
+    float4 nx0 = make_float4(0, 0, 0, 0), nx1 = nx0;
+    if (n_tiles > 0) {
+        nx0 = *reinterpret_cast<const float4*>(a + lane * 4);
+        nx1 = *reinterpret_cast<const float4*>(a + 128 + lane * 4);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        const float4 v0 = nx0, v1 = nx1;
+        if (t + 1 < n_tiles) {
+            nx0 = *reinterpret_cast<const float4*>(a + (size_t)(t + 1) * 256 + lane * 4);
+            nx1 = *reinterpret_cast<const float4*>(a + (size_t)(t + 1) * 256 + 128 + lane * 4);
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            s = __fadd_rn(s, __shfl_sync(full, v0.x, j));
+            s = __fadd_rn(s, __shfl_sync(full, v0.y, j));
+            s = __fadd_rn(s, __shfl_sync(full, v0.z, j));
+            s = __fadd_rn(s, __shfl_sync(full, v0.w, j));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            s = __fadd_rn(s, __shfl_sync(full, v1.x, j));
+            s = __fadd_rn(s, __shfl_sync(full, v1.y, j));
+            s = __fadd_rn(s, __shfl_sync(full, v1.z, j));
+            s = __fadd_rn(s, __shfl_sync(full, v1.w, j));
+        }
+    }
+    for (int base = n_tiles * 256; base < n; base += 32) {
+        const float v = base + lane < n ? a[base + lane] : 0.0f;
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(full, v, j));
     }
     if (lane == 0) centroid[e * 3 + comp] = __fdiv_rn(s, (float)n);
 }
 
-struct RigidDev {
-    float ax, ay, az;
-    double c, s, tx, ty, tz;
-};
-
 // ------------------------------------------------------------------------------------------------
 // K1 main kernel: slot s < P -> background point s; slot s >= P -> foreground point j = s - P.
 // ------------------------------------------------------------------------------------------------
-struct RigidBatch {
-    const dh_rigid* rigid;   // device copy, B entries
-};
-
 __global__ void __launch_bounds__(256) transform_project_kernel(
     const float* __restrict__ bg_depth, int P, int H, int W, CamDev cam, const dh_rigid* __restrict__ rigid,
     const float* __restrict__ xs, const float* __restrict__ ys,

@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(kLossThreads) guidance_loss_kernel(const __gri
         bg_term = fabsf(delta);
         const float sg = (float)((delta > 0.0f) - (delta < 0.0f));
         const float bscale = -sg * L.bgw / ((float)L.C * (float)p.n_bg_trans);
-        for (int n = tid; n < p.n_bg_trans; n += kLossThreads) gu[p.bg_trans[n]] += bscale;
+        // atomicAdd: a generic caller may list a cell twice; every addend is the same value, so the result does
+        // not depend on the order
+        for (int n = tid; n < p.n_bg_trans; n += kLossThreads) atomicAdd(gu + p.bg_trans[n], bscale);
     } else if (p.bg_kind == 2) {   // local_avg over the common background cells (losses.py:31-36)
         float a2 = 0.0f;
         const float bscale = L.bgw / ((float)L.C * (float)p.n_bg_common);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kLossThreads) guidance_loss_kernel(const __gri
             const int q = p.bg_common[n];
             const float df = uo[q] - uc[q];
             a2 += fabsf(df);
-            gu[q] += -(float)((df > 0.0f) - (df < 0.0f)) * bscale;
+            atomicAdd(gu + q, -(float)((df > 0.0f) - (df < 0.0f)) * bscale);
         }
         bg_term = block_sum_f(a2, red);
     }

@@ -120,32 +120,55 @@ __global__ void __launch_bounds__(256) splat_visible_kernel(const int32_t* __res
     visible[pi] = (fg && q >= 0 && winner[(size_t)e * P + q] == (uint32_t)i) ? 1 : 0;
 }
 
-// min / max of 1/depth over one image, one CTA per edit (deterministic, no atomics).
+// min / max of 1/depth over one image, one CTA per edit (deterministic, no atomics).  IEEE division is
+// monotone, so instead of dividing every pixel the kernel tracks min/max of the non-negative and of the
+// negative depths and takes the four reciprocals at the end: bit-identical to min/max over fl(1/d).
 __global__ void __launch_bounds__(1024) inv_minmax_kernel(const float* __restrict__ depth, int P, float* __restrict__ out) {
-    __shared__ float smin[32], smax[32];
+    __shared__ float sm[4][32];
     const int e = blockIdx.x;
     const float* d = depth + (size_t)e * P;
-    float mn = __int_as_float(0x7F800000), mx = -__int_as_float(0x7F800000);
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-        const float x = __fdiv_rn(1.0f, d[p]);
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
+    const float inf = __int_as_float(0x7F800000);
+    float pmin = inf, pmax = -inf, nmin = inf, nmax = -inf;     // over sign-bit-clear / sign-bit-set values
+    auto take = [&](float x) {
+        if (x != x) return;
+        if (__float_as_uint(x) & 0x80000000u) { nmin = fminf(nmin, x); nmax = fmaxf(nmax, x); }
+        else { pmin = fminf(pmin, x); pmax = fmaxf(pmax, x); }
+    };
+    const int P4 = ((reinterpret_cast<uintptr_t>(d) & 15) == 0) ? P / 4 : 0;
+    for (int i = threadIdx.x; i < P4; i += blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(d) + i);
+        take(v.x); take(v.y); take(v.z); take(v.w);
     }
+    for (int p = P4 * 4 + threadIdx.x; p < P; p += blockDim.x) take(d[p]);
+    float r[4] = {pmin, -pmax, nmin, -nmax};                      // all four as minima
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[k] = fminf(r[k], __shfl_xor_sync(0xFFFFFFFFu, r[k], o));
+        if (lane_id() == 0) sm[k][warp_id()] = r[k];
     }
-    if (lane_id() == 0) { smin[warp_id()] = mn; smax[warp_id()] = mx; }
     __syncthreads();
     if (warp_id() == 0) {
-        mn = smin[lane_id()]; mx = smax[lane_id()];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        for (int k = 0; k < 4; ++k) {
+            r[k] = lane_id() < (blockDim.x >> 5) ? sm[k][lane_id()] : inf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r[k] = fminf(r[k], __shfl_xor_sync(0xFFFFFFFFu, r[k], o));
         }
-        if (lane_id() == 0) { out[e * 2] = mn; out[e * 2 + 1] = mx; }
+        if (lane_id() == 0) {
+            pmin = r[0]; pmax = -r[1]; nmin = r[2]; nmax = -r[3];
+            float mn = inf, mx = -inf;
+            if (pmin <= pmax) {           // some non-negative depth: reciprocals in [1/pmax, 1/pmin]
+                mn = fminf(mn, __fdiv_rn(1.0f, pmax));
+                mx = fmaxf(mx, __fdiv_rn(1.0f, pmin));
+            }
+            if (nmin <= nmax) {           // some negative depth: reciprocals in [1/nmax, 1/nmin]
+                mn = fminf(mn, __fdiv_rn(1.0f, nmax));
+                mx = fmaxf(mx, __fdiv_rn(1.0f, nmin));
+            }
+            out[e * 2] = mn;
+            out[e * 2 + 1] = mx;
+        }
     }
 }
 

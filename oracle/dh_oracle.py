@@ -293,11 +293,13 @@ def morph_erode(img, el):
 
 def clean_target_mask(target_mask: np.ndarray, img_res: int,
                       close_el: Optional[np.ndarray] = None, open_el: Optional[np.ndarray] = None) -> np.ndarray:
-    """OPEN_{S//250}(CLOSE_{S//50}(mask)) with MORPH_ELLIPSE elements, depth_transform.py:308-321."""
+    """OPEN_{S//250}(CLOSE_{S//50}(mask)) with MORPH_ELLIPSE elements, depth_transform.py:308-321.
+    For S < 250 (S < 50) the reference's element size would be 0, which OpenCV rejects; the reference itself
+    only runs at S = 512.  Sizes are clamped to >= 1 (a 1x1 element is the identity) for those resolutions."""
     if close_el is None:
-        close_el = ellipse_element(img_res // 50)
+        close_el = ellipse_element(max(img_res // 50, 1))
     if open_el is None:
-        open_el = ellipse_element(img_res // 250)
+        open_el = ellipse_element(max(img_res // 250, 1))
     m = morph_erode(morph_dilate(target_mask, close_el), close_el)
     m = morph_dilate(morph_erode(m, open_el), open_el)
     return m

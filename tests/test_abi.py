@@ -108,3 +108,10 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(N.NativeLibraryError):
         pc = O.process_correspondences(np.zeros((0, 4), np.int64), 512)
         losses.compute_foreground_loss(torch.ones(2, 64, 64), torch.ones(2, 64, 64), pc, 1, (64, 64))
+
+
+def test_product_and_oracle_scene_generators_agree():
+    from diffusionhandles_b200.synthetic import synthetic_scene
+    for kw in (dict(S=64, seed=3), dict(S=128, seed=5, cx=40.0, cy=70.0, radius=30.0, quantize=0.1)):
+        for a, b in zip(synthetic_scene(**kw), O.synthetic_scene(**kw)):
+            assert np.array_equal(a, b)
