@@ -331,12 +331,13 @@ def run_ours(args):
     # ---- one NCCL gather of small per-edit result records (not on the hot path) ----
     gather_ms = None
     if world > 1:
+        from diffusionhandles_b200.batch import gather_records
         rec = torch.stack([wl["n_corr"].to(torch.int64), outs[0].flatten(1).sum(1).double().view(torch.int64)], dim=1).contiguous()
-        buf = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        dist.gather(rec, buf, dst=0)
+        gathered = gather_records(rec, dst=0)
         torch.cuda.synchronize(dev)
+        assert rank != 0 or gathered.shape[0] == world * n_edits
         gather_ms = 1e3 * (time.perf_counter() - t0)
 
     line = None

@@ -76,8 +76,12 @@ _SIGNATURES = {
     "dh_warp_gather_list": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dh_warp_gather_dense": (c_int, [C.POINTER(dh_warp_level), c_int, c_int, c_void_p]),
     "dh_guidance_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                 c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dh_loss_plan_bytes": (c_size_t, [c_int, c_int]),
+    "dh_loss_plan_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dh_build_loss_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                   c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "dh_poisson_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dh_poisson_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.c_double,

@@ -84,3 +84,20 @@ class EditWarpPipeline:
                 n_corr_h[e0:e1].copy_(res.n_corr, non_blocking=True)
         for slot in self.slots:
             slot["stream"].synchronize()
+
+
+def gather_records(records: torch.Tensor, dst: int = 0):
+    """One collective after a sharded sweep: gathers a fixed-size per-edit record tensor (n_local, k) from every
+    rank to ``dst`` and re-interleaves the rows into global edit order (edit e lives on rank e mod world).
+    Works with any torch.distributed backend (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = [torch.empty_like(records) for _ in range(world)] if rank == dst else None
+    dist.gather(records, buf, dst=dst)
+    if rank != dst:
+        return None
+    n_local = records.shape[0]
+    out = torch.empty((n_local * world,) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
+    for r in range(world):
+        out[r::world] = buf[r]
+    return out

@@ -229,6 +229,8 @@ using namespace dh;
 namespace {
 
 constexpr int kStagesDefault = 4;
+constexpr int kCtasPerSmDefault = 1;
+constexpr int kSegChunksDefault = 10;
 
 int sm_count_cached() {
     static int sms = 0;
@@ -250,6 +252,17 @@ bool fast_path_ok(const dh_warp_level& l) {
 
 }  // namespace
 
+template <int kStages>
+static int launch_dense(const WarpParams& p, int ctas_per_sm, cudaStream_t st) {
+    const size_t smem = (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t);
+    DH_CUDA_CHECK(cudaFuncSetAttribute(warp_dense_tma_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count_cached() * ctas_per_sm;
+    if (grid > p.total_segs) grid = p.total_segs;
+    warp_dense_tma_kernel<kStages><<<grid, kWarpThreads, smem, st>>>(p);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
 extern "C" {
 
 int dh_warp_gather_list(const float* in, int C, int hw, const int32_t* idx, int n, float* out, void* stream) {
@@ -261,19 +274,18 @@ int dh_warp_gather_list(const float* in, int C, int hw, const int32_t* idx, int 
     return DH_OK;
 }
 
-// Tunables (environment, read once): DH_WARP_CTAS_PER_SM, DH_WARP_SEG_CHUNKS.
+// Tunables (environment): DH_WARP_STAGES (2,3,4,6,8), DH_WARP_CTAS_PER_SM, DH_WARP_SEG_CHUNKS.
 int dh_warp_gather_dense(const dh_warp_level* levels_host, int n_levels, int B, void* stream) {
     DH_REQUIRE(levels_host && n_levels >= 1 && n_levels <= kMaxLevels && B >= 1);
     cudaStream_t st = as_stream(stream);
-    static int ctas_per_sm = 0, seg_chunks_cfg = 0;
-    if (ctas_per_sm == 0) {
-        const char* a = getenv("DH_WARP_CTAS_PER_SM");
-        const char* b = getenv("DH_WARP_SEG_CHUNKS");
-        ctas_per_sm = a ? atoi(a) : 3;
-        seg_chunks_cfg = b ? atoi(b) : 20;
-        if (ctas_per_sm < 1 || ctas_per_sm > 3) ctas_per_sm = 3;
-        if (seg_chunks_cfg < 1) seg_chunks_cfg = 20;
-    }
+    const char* ea = getenv("DH_WARP_CTAS_PER_SM");
+    const char* eb = getenv("DH_WARP_SEG_CHUNKS");
+    const char* ec = getenv("DH_WARP_STAGES");
+    int stages = ec ? atoi(ec) : kStagesDefault;
+    int ctas_per_sm = ea ? atoi(ea) : kCtasPerSmDefault;
+    int seg_chunks_cfg = eb ? atoi(eb) : kSegChunksDefault;
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = kCtasPerSmDefault;
+    if (seg_chunks_cfg < 1) seg_chunks_cfg = kSegChunksDefault;
     WarpParams p;
     memset(&p, 0, sizeof(p));
     int nfast = 0, seg = 0;
@@ -302,14 +314,13 @@ int dh_warp_gather_dense(const dh_warp_level* levels_host, int n_levels, int B, 
     if (nfast == 0) return DH_OK;
     p.n_levels = nfast;
     p.total_segs = seg;
-    constexpr int kStages = kStagesDefault;
-    const size_t smem = (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t);
-    DH_CUDA_CHECK(cudaFuncSetAttribute(warp_dense_tma_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = sm_count_cached() * ctas_per_sm;
-    if (grid > p.total_segs) grid = p.total_segs;
-    warp_dense_tma_kernel<kStages><<<grid, kWarpThreads, smem, st>>>(p);
-    DH_LAUNCH_CHECK();
-    return DH_OK;
+    switch (stages) {
+        case 2: return launch_dense<2>(p, ctas_per_sm, st);
+        case 3: return launch_dense<3>(p, ctas_per_sm, st);
+        case 6: return launch_dense<6>(p, ctas_per_sm, st);
+        case 8: return launch_dense<8>(p, ctas_per_sm, st);
+        default: return launch_dense<4>(p, ctas_per_sm, st);
+    }
 }
 
 }  // extern "C"

@@ -1,0 +1,81 @@
+"""``DiffusionHandles`` facade with the reference's method names and signatures (diffusion_handles.py:13-166).
+
+The geometry half of ``transform_foreground`` (:143-149) runs on the sm_100a kernels of this package.  The
+diffusion half (U-Net, VAE, text encoder, scheduler, null-text inversion) is stock PyTorch/diffusers code that this
+build deliberately does not re-implement (north star): it is injected as ``diffuser`` / ``inverter`` objects that
+expose the reference's ``initial_inference`` / ``guided_inference`` / ``invert`` methods.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from .depth_transform import normalize_depth, transform_depth
+from .guided_stable_diffuser import GuidedStableDiffuser
+
+DEFAULT_CONF = SimpleNamespace(   # diffhandles/config/default.yaml
+    guided_diffuser=SimpleNamespace(bg_weight=1.25, fg_weight=1.5, fg_patch_size=1, bg_patch_size=1, use_depth=True,
+                                    save_denoising_steps=False, bg_loss_type='global_avg', num_timesteps=50, num_optsteps=3,
+                                    guidance_max_step=38, guidance_schedule_type='constant', bg_erosion=0, seed=2773),
+    depth_transform_mode='pc')
+
+
+class DiffusionHandles:
+    def __init__(self, conf=None, diffuser=None, inverter=None):
+        self.conf = DEFAULT_CONF if conf is None else conf
+        self.diffuser = GuidedStableDiffuser(conf=self.conf.guided_diffuser) if diffuser is None else diffuser
+        self.inverter = inverter
+        self.device = torch.device('cpu')
+
+    def to(self, device: torch.device = None):
+        self.diffuser.to(device=device)
+        if self.inverter is not None:
+            self.inverter.to(device=device)
+        self.device = device
+        return self
+
+    def _need(self, obj, method):
+        if obj is None or not hasattr(obj, method):
+            raise NotImplementedError(
+                f"{method} needs the stock-PyTorch diffusion model (U-Net / VAE / scheduler), which is outside this build; "
+                "pass a diffuser / inverter object that implements it")
+        return getattr(obj, method)
+
+    def invert_input_image(self, img: torch.Tensor, depth: torch.Tensor, prompt: str):
+        disparity = normalize_depth(1.0 / depth)
+        _, init_noise, null_text_emb = self._need(self.inverter, "invert")(
+            target_img=img, depth=disparity, prompt=prompt, num_inner_steps=5, verbose=True)
+        return null_text_emb, init_noise
+
+    def generate_input_image(self, depth: torch.Tensor, prompt: str, null_text_emb: torch.Tensor = None,
+                             init_noise: torch.Tensor = None):
+        disparity = normalize_depth(1.0 / depth)
+        with torch.no_grad():
+            activations, latent_image, null_text_emb, init_noise = self._need(self.diffuser, "initial_inference")(
+                init_latents=init_noise, depth=disparity, uncond_embeddings=null_text_emb, prompt=prompt)
+        return null_text_emb, init_noise, activations, latent_image
+
+    def set_foreground(self, depth: torch.Tensor, fg_mask: torch.Tensor, bg_depth: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("set_foreground (solve_laplacian_depth pre-processing) is a 'next' row, SURVEY.md 8(f) rank 1")
+
+    def transform_foreground(self, depth: torch.Tensor, prompt: str, fg_mask: torch.Tensor, bg_depth: torch.Tensor,
+                             null_text_emb: torch.Tensor, init_noise: torch.Tensor, activations: list,
+                             rot_angle: float = None, rot_axis: torch.Tensor = None, translation: torch.Tensor = None,
+                             fg_weight: float = None, bg_weight: float = None, use_input_depth_normalization=False):
+        with torch.no_grad():
+            edited_disparity, correspondences = transform_depth(
+                depth=depth, bg_depth=bg_depth, fg_mask=fg_mask,
+                intrinsics=self.diffuser.get_depth_intrinsics(device=depth.device),
+                rot_angle=rot_angle, rot_axis=rot_axis, translation=translation,
+                use_input_depth_normalization=use_input_depth_normalization,
+                depth_transform_mode=self.conf.depth_transform_mode)
+        with torch.no_grad():
+            results = self._need(self.diffuser, "guided_inference")(
+                latents=init_noise, depth=edited_disparity, uncond_embeddings=null_text_emb, prompt=prompt,
+                activations_orig=activations, correspondences=correspondences, fg_weight=fg_weight, bg_weight=bg_weight,
+                save_denoising_steps=self.conf.guided_diffuser.save_denoising_steps)
+        if self.conf.guided_diffuser.save_denoising_steps:
+            edited_img, denoising_steps = results
+            return edited_img, edited_disparity, denoising_steps
+        return results, edited_disparity

@@ -37,9 +37,47 @@ def _lists(pc, grid: int, device) -> Dict[str, torch.Tensor]:
     }
 
 
+class LossPlan:
+    """Device-side loss plan (dh_build_loss_plan): CSR of distinct (src,dst) cell pairs per destination cell with
+    multiplicities + per-cell multiplicities of the background lists.  Built once per edit, reused every step."""
+
+    def __init__(self, grid: int, device, fg_src=None, fg_dst=None, bg_orig=None, bg_trans=None, bg_common=None):
+        lib = N.load()
+        self.grid = grid
+        self.n = [int(t.numel()) if t is not None else 0 for t in (fg_src, bg_orig, bg_trans, bg_common)]
+        n_fg = self.n[0]
+        plan_bytes = int(lib.dh_loss_plan_bytes(grid, n_fg))
+        ws_bytes = int(lib.dh_loss_plan_workspace_bytes(grid, n_fg))
+        if plan_bytes == 0:
+            raise NotImplementedError(f"loss grids larger than 64 x 64 are not implemented (got {grid})")
+        self.buf = torch.empty(plan_bytes, dtype=torch.uint8, device=device)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+
+        def p(t):
+            return N.ptr(t, torch.int32) if t is not None and t.numel() else None
+        N.check(lib.dh_build_loss_plan(p(fg_src), p(fg_dst), n_fg, p(bg_orig), self.n[1], p(bg_trans), self.n[2], p(bg_common),
+                                       self.n[3], grid, N.ptr(self.buf), plan_bytes, N.ptr(ws), ws_bytes,
+                                       N.stream_handle(torch.device(device))), "dh_build_loss_plan")
+
+
+def _plan_for(pc, grid: int, device, keys=("fg_src", "fg_dst", "bg_orig", "bg_trans", "bg")) -> LossPlan:
+    """The (cached) plan of a processed-correspondences dict."""
+    cache = getattr(pc, "_loss_plans", None) if isinstance(pc, ProcessedCorrespondences) else None
+    key = (grid, str(device))
+    if cache is not None and key in cache:
+        return cache[key]
+    ls = _lists(pc, grid, device)
+    plan = LossPlan(grid, device, ls["fg_src"], ls["fg_dst"], ls["bg_orig"], ls["bg_trans"], ls["bg"])
+    if isinstance(pc, ProcessedCorrespondences):
+        if cache is None:
+            pc._loss_plans = {}
+        pc._loss_plans[key] = plan
+    return plan
+
+
 def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_grad: Sequence[bool],
-            fgw: Sequence[float], bgw: Sequence[float], grid: int, fg_src, fg_dst, bg_orig, bg_trans, bg_common,
-            fg_kind: int, bg_kind: int) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+            fgw: Sequence[float], bgw: Sequence[float], plan: LossPlan, fg_kind: int,
+            bg_kind: int) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
     lib = N.load()
     dev = curs[0].device
     if dev.type != "cuda":
@@ -61,19 +99,12 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         layers[i].channels, layers[i].h, layers[i].w = c32.shape
         layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
     total_c = sum(int(c.shape[0]) for c in curs)
-    ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(int(c.shape[0]) for c in curs)))
-    ws_bytes = max(ws_bytes, 8 * total_c)
+    ws_bytes = 8 * total_c + 64
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
-
-    def p(t):
-        return N.ptr(t, torch.int32) if t is not None and t.numel() else None
-
-    def n(t):
-        return int(t.numel()) if t is not None else 0
-    N.check(lib.dh_guidance_loss(layers, L, grid, p(fg_src), p(fg_dst), n(fg_src), p(bg_orig), n(bg_orig), p(bg_trans),
-                                 n(bg_trans), p(bg_common), n(bg_common), fg_kind, bg_kind, N.ptr(out), N.ptr(ws), ws_bytes,
-                                 N.stream_handle(dev)), "dh_guidance_loss")
+    n_fg, n_bo, n_bt, n_bc = plan.n
+    N.check(lib.dh_guidance_loss(layers, L, plan.grid, N.ptr(plan.buf), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind, N.ptr(out),
+                                 N.ptr(ws), ws_bytes, N.stream_handle(dev)), "dh_guidance_loss")
     return out, grads
 
 
@@ -83,8 +114,7 @@ class _FusedLoss(torch.autograd.Function):
         L = spec["L"]
         curs, origs = acts[:L], acts[L:]
         want = [ctx.needs_input_grad[1 + i] for i in range(L)]
-        out, grads = _launch(curs, origs, want, spec["fgw"], spec["bgw"], spec["grid"], spec.get("fg_src"), spec.get("fg_dst"),
-                             spec.get("bg_orig"), spec.get("bg_trans"), spec.get("bg_common"), spec["fg_kind"], spec["bg_kind"])
+        out, grads = _launch(curs, origs, want, spec["fgw"], spec["bgw"], spec["plan"], spec["fg_kind"], spec["bg_kind"])
         ctx.grads = grads
         ctx.n_inputs = len(acts)
         total, parts = out[0].clone(), out[1:].clone()
@@ -123,10 +153,8 @@ def guidance_loss(activations: Sequence[torch.Tensor], activations_orig: Sequenc
         raise ValueError(f'Unknown background loss type: {bg_loss_type}')
     grid = _grid_of(activations_size)
     dev = activations[0].device
-    ls = _lists(processed_correspondences, grid, dev)
-    spec = dict(L=len(activations), fgw=list(fg_weights), bgw=list(bg_weights), grid=grid, fg_src=ls["fg_src"], fg_dst=ls["fg_dst"],
-                bg_orig=ls["bg_orig"], bg_trans=ls["bg_trans"], bg_common=ls["bg"], fg_kind=_FG,
-                bg_kind=_BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL)
+    spec = dict(L=len(activations), fgw=list(fg_weights), bgw=list(bg_weights), plan=_plan_for(processed_correspondences, grid, dev),
+                fg_kind=_FG, bg_kind=_BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL)
     return _FusedLoss.apply(spec, *activations, *activations_orig)
 
 
@@ -135,8 +163,7 @@ def compute_foreground_loss(activations, activations_orig, processed_corresponde
     if patch_size != 1:
         raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
     grid = _grid_of(activations_size)
-    ls = _lists(processed_correspondences, grid, activations.device)
-    spec = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=ls["fg_src"], fg_dst=ls["fg_dst"], fg_kind=_FG, bg_kind=0)
+    spec = dict(L=1, fgw=[1.0], bgw=[0.0], plan=_plan_for(processed_correspondences, grid, activations.device), fg_kind=_FG, bg_kind=0)
     return _FusedLoss.apply(spec, activations, activations_orig)[0]
 
 
@@ -148,8 +175,7 @@ def compute_background_loss(activations, activations_orig, processed_corresponde
     if loss_type == 'local_avg' and patch_size != 1:
         raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
     grid = _grid_of(activations_size)
-    ls = _lists(processed_correspondences, grid, activations.device)
-    spec = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=ls["bg_orig"], bg_trans=ls["bg_trans"], bg_common=ls["bg"],
+    spec = dict(L=1, fgw=[0.0], bgw=[1.0], plan=_plan_for(processed_correspondences, grid, activations.device),
                 fg_kind=0, bg_kind=_BG_GLOBAL if loss_type == 'global_avg' else _BG_LOCAL)
     return _FusedLoss.apply(spec, activations, activations_orig)[0]
 
@@ -169,8 +195,8 @@ def average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2):
     grid = _grid_of(feat_map_1.shape[-2:])
     dev = feat_map_2.device
     a, b = _to_cells(y1, x1, grid, dev), _to_cells(y2, x2, grid, dev)
-    fwd = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=a, bg_trans=b, fg_kind=0, bg_kind=_BG_GLOBAL)
-    swp = dict(L=1, fgw=[0.0], bgw=[1.0], grid=grid, bg_orig=b, bg_trans=a, fg_kind=0, bg_kind=_BG_GLOBAL)
+    fwd = dict(L=1, fgw=[0.0], bgw=[1.0], plan=LossPlan(grid, dev, bg_orig=a, bg_trans=b), fg_kind=0, bg_kind=_BG_GLOBAL)
+    swp = dict(L=1, fgw=[0.0], bgw=[1.0], plan=LossPlan(grid, dev, bg_orig=b, bg_trans=a), fg_kind=0, bg_kind=_BG_GLOBAL)
     return _two_sided(fwd, swp, feat_map_1, feat_map_2)
 
 
@@ -181,6 +207,6 @@ def local_average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2, patch_siz
     grid = _grid_of(feat_map_1.shape[-2:])
     dev = feat_map_2.device
     a, b = _to_cells(y1, x1, grid, dev), _to_cells(y2, x2, grid, dev)
-    fwd = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=a, fg_dst=b, fg_kind=_FG, bg_kind=0)
-    swp = dict(L=1, fgw=[1.0], bgw=[0.0], grid=grid, fg_src=b, fg_dst=a, fg_kind=_FG, bg_kind=0)
+    fwd = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=a, fg_dst=b), fg_kind=_FG, bg_kind=0)
+    swp = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=b, fg_dst=a), fg_kind=_FG, bg_kind=0)
     return _two_sided(fwd, swp, feat_map_1, feat_map_2)

@@ -196,11 +196,20 @@ typedef struct dh_loss_layer {
     float fg_weight, bg_weight;
 } dh_loss_layer;
 
+/* Loss plan, built once per edit from the process_correspondences lists (int32 cell ids y*grid+x): the
+ * foreground pairs grouped by destination cell with duplicates collapsed into multiplicities, and the per-cell
+ * multiplicities of the three background lists.  grid <= 64.  plan / ws sizes from the two queries. */
+size_t dh_loss_plan_bytes(int grid, int n_fg);
+size_t dh_loss_plan_workspace_bytes(int grid, int n_fg);
+int dh_build_loss_plan(const int32_t* fg_src, const int32_t* fg_dst, int n_fg,
+                       const int32_t* bg_orig, int n_bg_orig, const int32_t* bg_trans, int n_bg_trans,
+                       const int32_t* bg_common, int n_bg_common, int grid,
+                       void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
+
 size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels);
-int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid,
-                     const int32_t* fg_src, const int32_t* fg_dst, int n_fg,
-                     const int32_t* bg_orig, int n_bg_orig, const int32_t* bg_trans, int n_bg_trans,
-                     const int32_t* bg_common, int n_bg_common, int fg_kind, int bg_kind,
+/* n_* are the list lengths the plan was built from (they are the means' denominators). */
+int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan,
+                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind,
                      float* loss_out /* device float[1 + 2*n_layers]: total, then fg_l, bg_l */,
                      void* ws, size_t ws_bytes, void* stream);
 /* grads *= *scale (device scalar); exits early on the device when *scale == 1. */

@@ -573,6 +573,34 @@ def background_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray]
     return dtype(loss), bilinear_resize_transpose(g_up, (h, w), dtype)
 
 
+def loss_sign_ambiguity(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray], size=(64, 64),
+                        bg_loss_type: str = "global_avg", eps: float = 2e-6) -> np.ndarray:
+    """bool (C,h,w): native cells whose gradient depends on sign(d) of a difference with |d| < eps.
+
+    The losses are L1: their gradient is a sum of +-1/(C N) terms.  Where a difference is within fp32 rounding
+    of zero, its sign - and with it one gradient quantum - legitimately depends on the arithmetic (fp32 vs fp64,
+    FMA contraction); the reference itself differs between its CPU and CUDA runs there.  Parity tests compare the
+    gradients on the complement of this mask and require the mask to be a vanishing fraction of the tensor."""
+    C, h, w = cur.shape
+    uo = bilinear_resize(orig, size, f64)
+    uc = bilinear_resize(cur, size, f64)
+    amb_up = np.zeros((C, size[0] * size[1]), bool)
+    if len(pc["original_x"]):
+        d = uo[:, pc["original_y"], pc["original_x"]] - uc[:, pc["transformed_y"], pc["transformed_x"]]
+        cell = pc["transformed_y"] * size[1] + pc["transformed_x"]
+        cc, nn = np.nonzero(np.abs(d) < eps)
+        amb_up[cc, cell[nn]] = True
+    if bg_loss_type == "local_avg":
+        d = uo[:, pc["background_y"], pc["background_x"]] - uc[:, pc["background_y"], pc["background_x"]]
+        cc, nn = np.nonzero(np.abs(d) < eps)
+        amb_up[cc, (pc["background_y"] * size[1] + pc["background_x"])[nn]] = True
+    amb = bilinear_resize_transpose(amb_up.reshape(C, *size).astype(f64), (h, w), f64) > 0
+    if bg_loss_type == "global_avg" and len(pc["background_x_orig"]) and len(pc["background_x_trans"]):
+        delta = uo[:, pc["background_y_orig"], pc["background_x_orig"]].mean(-1) - uc[:, pc["background_y_trans"], pc["background_x_trans"]].mean(-1)
+        amb[np.abs(delta) < eps] = True
+    return amb
+
+
 def guidance_weight_schedule(fg_weight: float = 1.5, bg_weight: float = 1.25, guidance_max_step: int = 38,
                              schedule_type: str = "constant"):
     """guided_stable_diffuser.py:336-373 + StepGuidanceWeightSchedule :622-665 as a function (t_idx, it) -> (fgw, bgw)."""

@@ -303,9 +303,16 @@ def test_warp_full_stack_properties(dev):
         assert torch.equal(o.flatten(2), ref)
 
 
-def _loss_check(val, grad, ref_v, ref_g, key):
+def _loss_check(val, grad, ref_v, ref_g, key, ambiguous=None):
+    """1e-5 relative (fp32) on the value and on the gradient (max-norm relative to the largest gradient entry).
+    Cells whose gradient hinges on the sign of a difference within fp32 rounding of zero (oracle.loss_sign_ambiguity)
+    are excluded from the gradient comparison; they must be a vanishing fraction."""
     assert abs(val - ref_v) <= 1e-5 * abs(ref_v), (key, val, ref_v)
-    assert np.abs(grad - ref_g).max() <= 1e-5 * np.abs(ref_g).max(), key
+    diff = np.abs(grad - ref_g)
+    if ambiguous is not None:
+        assert ambiguous.mean() < 1e-4, (key, ambiguous.mean())
+        diff = np.where(ambiguous, 0.0, diff)
+    assert diff.max() <= 1e-5 * np.abs(ref_g).max(), (key, diff.max(), np.abs(ref_g).max())
 
 
 @pytest.mark.parametrize("tag", ["c6h64", "c5h32", "c3h16"])
@@ -318,18 +325,19 @@ def test_losses_golden(dev, golden_small, golden_pc, tag):
     pc = GuidedStableDiffuser().process_correspondences(torch.from_numpy(gp["cfg1/corr"].astype(np.int64)), 512, 0)
     pc_np = O.process_correspondences(gp["cfg1/corr"].astype(np.int64), 512, 0)
     orig = torch.from_numpy(g[f"loss_{tag}/orig"]).to(dev)
+    amb = {lt: O.loss_sign_ambiguity(g[f"loss_{tag}/cur"], g[f"loss_{tag}/orig"], pc_np, bg_loss_type=lt) for lt in ("global_avg", "local_avg")}
     for use_plain_dict in (False, True):
         p = pc_np if use_plain_dict else pc
         cur = torch.from_numpy(g[f"loss_{tag}/cur"]).to(dev).requires_grad_(True)
         lf = losses.compute_foreground_loss(cur, orig, p, 1, (64, 64))
         assert lf.dim() == 0 and lf.dtype == torch.float32
         gf = torch.autograd.grad(lf, cur)[0]
-        _loss_check(lf.item(), gf.cpu().numpy(), g[f"loss_{tag}/fg"], g[f"loss_{tag}/fg_grad"], "fg")
+        _loss_check(lf.item(), gf.cpu().numpy(), g[f"loss_{tag}/fg"], g[f"loss_{tag}/fg_grad"], "fg", amb["global_avg"])
         for lt in ("global_avg", "local_avg"):
             cur = torch.from_numpy(g[f"loss_{tag}/cur"]).to(dev).requires_grad_(True)
             lb = losses.compute_background_loss(cur, orig, p, 1, (64, 64), loss_type=lt)
             gb = torch.autograd.grad(lb, cur)[0]
-            _loss_check(lb.item(), gb.cpu().numpy(), g[f"loss_{tag}/bg_{lt}"], g[f"loss_{tag}/bg_{lt}_grad"], lt)
+            _loss_check(lb.item(), gb.cpu().numpy(), g[f"loss_{tag}/bg_{lt}"], g[f"loss_{tag}/bg_{lt}_grad"], lt, amb[lt])
     with pytest.raises(ValueError):
         losses.compute_background_loss(cur, orig, pc, 1, (64, 64), loss_type="nope")
 
@@ -365,8 +373,10 @@ def test_fused_guidance_loss_config3(dev, golden_pc):
             assert abs(parts[2 * l].item() - vf) <= 1e-5 * abs(vf)
             assert abs(parts[2 * l + 1].item() - vb) <= 1e-5 * abs(vb)
         assert abs(total.item() - ref_total) <= 1e-5 * abs(ref_total)
-        for a, b in zip(grads, ref_grads):
-            assert np.abs(a.cpu().numpy() - b).max() <= 1e-5 * np.abs(b).max()
+        for a, b, c, o_ in zip(grads, ref_grads, curs, origs):
+            amb = O.loss_sign_ambiguity(c.numpy(), o_.numpy(), pc_np, bg_loss_type=lt)
+            assert amb.mean() < 1e-4
+            assert np.where(amb, 0.0, np.abs(a.cpu().numpy() - b)).max() <= 1e-5 * np.abs(b).max()
         # bit-reproducible (integer sign counts): a second evaluation gives identical bits
         dc2 = [c.to(dev).requires_grad_(True) for c in curs]
         total2, _ = losses.guidance_loss(dc2, [o.to(dev) for o in origs], pc, fgw, bgw, bg_loss_type=lt)
@@ -404,3 +414,65 @@ def test_no_cpu_fallback(dev):
     d = torch.ones(1, 1, 8, 8)
     with pytest.raises(N.NativeLibraryError):
         dt.depth_to_world_coords(d, torch.eye(3))
+
+
+def test_splat_renderer_interface(dev, K):
+    """Renderer interface (renderer.py:20-60): scene of [bg mesh, fg mesh] + camera -> world_position and
+    flat_vertex_color layers; the per-pixel winner must equal the oracle's z-buffer over the same vertices."""
+    import diffusionhandles_b200 as pkg
+    pkg.install_as_diffhandles()
+    from diffhandles.renderer import Camera, Renderer
+    from diffhandles.pytorch3d_renderer import PyTorch3DRenderer, PyTorch3DRendererArgs
+    from diffhandles.mesh import Mesh
+    from diffhandles import depth_transform as dt
+    S = 96
+    depth, bg, mask = O.synthetic_scene(S, 31)
+    bgp = dt.depth_to_world_coords(torch.from_numpy(bg).to(dev)[None, None], K).reshape(-1, 3)
+    fgp = dt.depth_to_world_coords(torch.from_numpy(depth).to(dev)[None, None], K).reshape(-1, 3)[torch.from_numpy(mask.reshape(-1) > 0).to(dev)]
+    fgp = fgp + torch.tensor([0.2, 0.0, -0.1], device=dev)
+    faces = torch.zeros((0, 3), dtype=torch.int64)
+    mb, mf = Mesh(bgp, faces), Mesh(fgp, faces)
+    mb.add_vert_attribute("color", torch.cat([torch.rand(bgp.shape[0], 2, device=dev), torch.zeros(bgp.shape[0], 1, device=dev)], 1))
+    mf.add_vert_attribute("color", torch.cat([torch.rand(fgp.shape[0], 2, device=dev), torch.ones(fgp.shape[0], 1, device=dev)], 1))
+    r = PyTorch3DRenderer(output_names=['world_position', 'flat_vertex_color'],
+                          args=PyTorch3DRendererArgs(device=dev, output_res=(S, S), cull_backfaces=True, blur_radius=1e-5))
+    assert isinstance(r, Renderer)
+    r.update_scene(scene_elements={'meshes': [mb, mf], 'cameras': [Camera(intrinsics=K)]})
+    out = r.render()
+    assert out['world_position'].shape == (1, S, S, 4) and out['flat_vertex_color'].shape == (1, S, S, 4)
+    allp = torch.cat([bgp, fgp]).double().cpu().numpy()
+    pm = np.concatenate([np.zeros(bgp.shape[0], np.uint8), np.ones(fgp.shape[0], np.uint8)])
+    dm, mk, _, _, _, winner = O.points_to_depth(allp, K_NP, (S, S), pm)
+    assert np.array_equal(out['world_position'][0, ..., 2].cpu().numpy(), np.where(np.isinf(dm), 0, dm))
+    assert np.array_equal(out['flat_vertex_color'][0, ..., 2].cpu().numpy() > 0.5, mk)
+    with pytest.raises(RuntimeError):
+        r.set_output_layers(['flat_texture_nope'])
+    with pytest.raises(RuntimeError):
+        r.update_scene({'lights': []})
+    with pytest.raises(RuntimeError):
+        r.update_scene({'meshes': [object()]})
+
+
+def test_diffusion_handles_facade_transform_foreground(dev, K, golden_pc):
+    """DiffusionHandles.transform_foreground (diffusion_handles.py:110-166) with an injected stand-in for the
+    stock-PyTorch diffuser: the geometry half must hand the reference's correspondences to guided_inference."""
+    from diffusionhandles_b200 import DiffusionHandles
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
+    meta, g = golden_pc
+    m = meta["cfg1"]
+
+    class FakeDiffuser(GuidedStableDiffuser):
+        def guided_inference(self, latents, depth, uncond_embeddings, prompt, activations_orig, correspondences,
+                             fg_weight=None, bg_weight=None, save_denoising_steps=False):
+            self.seen = (depth, correspondences)
+            return torch.zeros(1, 3, 8, 8)
+
+    dh = DiffusionHandles(diffuser=FakeDiffuser()).to(dev)
+    depth, bg, mask = O.synthetic_scene(**m["scene"])
+    td, tb, tm = (torch.from_numpy(a).to(dev)[None, None] for a in (depth, bg, mask))
+    img, disp = dh.transform_foreground(td, "a prompt", tm, tb, None, None, [], rot_angle=m["angle"],
+                                        rot_axis=torch.tensor(m["axis"]), translation=torch.tensor(m["translation"]))
+    assert np.array_equal(dh.diffuser.seen[1].numpy(), g["cfg1/corr"].astype(np.int64))
+    assert disp.shape == (1, 1, 512, 512)
+    with pytest.raises(NotImplementedError):
+        DiffusionHandles().generate_input_image(td, "x")
