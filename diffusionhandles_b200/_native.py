@@ -38,7 +38,7 @@ class dh_warp_level(C.Structure):
 
 class dh_loss_layer(C.Structure):
     _fields_ = [("cur", c_void_p), ("orig", c_void_p), ("grad", c_void_p), ("channels", C.c_int32), ("h", C.c_int32),
-                ("w", C.c_int32), ("fg_weight", c_float), ("bg_weight", c_float)]
+                ("w", C.c_int32), ("fg_weight", c_float), ("bg_weight", c_float), ("resize_tables", c_void_p)]
 
 
 _SIGNATURES = {
@@ -76,11 +76,14 @@ _SIGNATURES = {
     "dh_warp_gather_list": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dh_warp_gather_dense": (c_int, [C.POINTER(dh_warp_level), c_int, c_int, c_void_p]),
     "dh_guidance_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dh_loss_resize_tables_bytes": (c_size_t, []),
+    "dh_build_loss_resize_tables": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dh_loss_plan_bytes": (c_size_t, [c_int, c_int]),
     "dh_loss_plan_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dh_build_loss_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
-    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+    "dh_loss_plan_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
+    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "dh_poisson_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

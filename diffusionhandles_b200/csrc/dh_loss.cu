@@ -25,15 +25,13 @@
 
 namespace dh {
 
-constexpr int kLossThreads = 1024;
-constexpr int kLossWarps = kLossThreads / 32;
 constexpr int kMaxLossLayers = 8;
 constexpr int kMaxG = 64;
-constexpr int kMaxCells = kMaxG * kMaxG;          // 4096
 constexpr int kMaxNative = 64;
 
 struct PlanHeader {
     int32_t n_pairs, n_fg, n_bg_orig, n_bg_trans, n_bg_common, grid, cap, reserved;
+    int32_t box_r0, box_r1, box_s0, box_s1;   // box (loss-grid rows / columns) of the cells that are a pair source or destination
 };
 
 struct PlanView {
@@ -163,6 +161,9 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     for (int i = tid; i < 4 * cells; i += kPlanThreads) psm[i] = 0;
     __syncthreads();
     for (int n = tid; n < n_fg; n += kPlanThreads) is_src[fg_src[n]] = 1;
+    __shared__ int box_sm[4];
+    __shared__ int nonbin_sm;
+    if (tid == 0) { box_sm[0] = grid; box_sm[1] = -1; box_sm[2] = grid; box_sm[3] = -1; nonbin_sm = 0; }
     for (int n = tid; n < n_bg_orig; n += kPlanThreads) atomicAdd(co + bg_orig[n], 1);
     for (int n = tid; n < n_bg_trans; n += kPlanThreads) atomicAdd(ct + bg_trans[n], 1);
     for (int n = tid; n < n_bg_common; n += kPlanThreads) atomicAdd(cc + bg_common[n], 1);
@@ -172,19 +173,46 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
         v.x = (unsigned short)min(co[i], 65535); v.y = (unsigned short)min(ct[i], 65535);
         v.z = (unsigned short)min(cc[i], 65535); v.w = (unsigned short)(is_src[i] ? 1 : 0);
         pv.bgcnt[i] = v;
+        if (co[i] > 1 || ct[i] > 1 || cc[i] > 1) nonbin_sm = 1;
+        if (is_src[i] || pv.row_ptr[i + 1] > pv.row_ptr[i]) {
+            const int r = i / grid, c = i - r * grid;
+            atomicMin(box_sm + 0, r); atomicMax(box_sm + 1, r); atomicMin(box_sm + 2, c); atomicMax(box_sm + 3, c);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pv.hdr->box_r0 = box_sm[0]; pv.hdr->box_r1 = box_sm[1]; pv.hdr->box_s0 = box_sm[2]; pv.hdr->box_s1 = box_sm[3];
+        pv.hdr->reserved = nonbin_sm ? 0 : 1;      // bit 0: every background multiplicity is 0 or 1
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // fused loss + gradient
 // ------------------------------------------------------------------------------------------------
+// Two kernels share one design: small CTAs (256 threads), many per SM, each walking over (layer, channel) planes.
+//   loss_flat_kernel    layers that already have the loss-grid resolution (64x64): the planes are read straight from
+//                       global memory with 128-bit loads (every cell is needed exactly once for the background sums
+//                       and the gradient), the pair gathers hit the same 32 KB in L1.
+//   loss_resize_kernel  smaller layers (32x32, ...): both planes are staged in shared memory, resized bilinearly
+//                       only inside the box that contains pair cells; the background sums are inner products with
+//                       up^T(multiplicity) at native resolution; the gradient is gathered back through up^T.
+// The sign terms of the foreground pairs are accumulated as INTEGERS (shared-memory atomics): integer addition is
+// associative, so the gradient is bit-reproducible (the reference's index_put(accumulate=True) is not, on CUDA).
+// The last CTA of the last kernel reduces the per-channel partial sums in a fixed order.
+constexpr int kLossThreads = 256;
+constexpr int kLossWarps = kLossThreads / 32;
+constexpr int kOwnGroups = kMaxG * kMaxG / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
+constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): 2 * G / h <= 16 for h >= 8
+
 struct LossLayerDev {
     const float* cur;
     const float* orig;
     float* grad;
     int C, h, w;
     float fgw, bgw;
-    int chan_begin;     // first global channel id of this layer
+    const void* tab;      // LayerTab of a resized layer (NULL for layers at the loss-grid resolution)
+    int chan_begin;       // first channel id of this layer inside the kernel's own channel range
+    int partial_begin;    // first channel id of this layer in the partial-sum array (all layers)
 };
 
 struct LossParams {
@@ -195,34 +223,28 @@ struct LossParams {
     int n_fg, n_bg_orig, n_bg_trans, n_bg_common;
     int fg_kind;        // 0 = off, 1 = local_avg patch 1
     int bg_kind;        // 0 = off, 1 = global_avg, 2 = local_avg
-    float* partial;     // [total_channels][2]: fg sum, bg term
+    float* partial;     // [all channels][2]: fg sum, bg term
 };
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct LossFinal {
+    int n_layers, C[kMaxLossLayers], partial_begin[kMaxLossLayers];
+    float fgw[kMaxLossLayers], bgw[kMaxLossLayers];
+    unsigned int* done_counter;       // zeroed before the launches
+    unsigned int total_ctas;          // CTAs of both kernels
+    float* loss_out;
+};
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
+struct ResizeLayout {   // float offsets into dynamic shared memory
+    int tab, wo, wt, planes, uc, uo, cnt, tmp, total;
+    int box_cap;        // capacity (cells) of the box-local uc / uo / cnt arrays
+};
+
+__device__ __forceinline__ int layer_of(const LossParams& p, int gc) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLossLayers; ++i)
+        if (i < p.n_layers && gc >= p.lv[i].chan_begin) l = i;
+    return l;
 }
 
 // torch area_pixel_compute_source_index (align_corners = False) for output index i
@@ -235,47 +257,7 @@ __device__ __forceinline__ void bilinear_tap(int i, int n_in, float scale, int& 
     lam = src - (float)i0;
 }
 
-// Shared-memory carve-up (floats unless noted), sized by the launch from the layer shapes:
-//   stage[2][2][hw_max]   double-buffered current / recorded plane at native resolution (TMA destination)
-//   cnt[GG] (int)         per destination cell: - sum mult * sign(d); rewritten in place as the float gradient
-//   pairs[cap] (uint2)    the plan's (src | dst << 16, mult) entries when they fit
-//   -- only when a layer is smaller than the loss grid --
-//   uc[GG], uo[GG]        up(cur), up(orig) inside the active box
-//   tmp[h_max * G]        separable transposed resize
-//   wo[hw_r], wt[hw_r]    up^T(background multiplicities) at native resolution
-//   wrow[h_max][kWin], wcol[w_max][kWin]   transposed-resize weights per native row / column
-struct LossSmemLayout {
-    int stage, stage_stride, cnt, pairs, pairs_cap, uc, uo, tmp, wo, wt, wrow, wcol, total_floats;
-};
-
-constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): G/h * 2 <= 16 for h >= 8
-
-struct LossTables {
-    float red[kLossWarps][4];
-    int ty0[kMaxG], ty1[kMaxG], tx0[kMaxG], tx1[kMaxG];
-    float tly[kMaxG], tlx[kMaxG];
-    int ylo[kMaxNative], yhi[kMaxNative], xlo[kMaxNative], xhi[kMaxNative];
-    int box[8];                        // active box in up space: r0, r1, s0, s1; native: y0, y1, x0, x1
-    int flags[2];
-    int scratch[kLossWarps * 8];
-    float lconst[kMaxLossLayers][4];   // per layer: fscale, lscale, bgw / (C * n_bg_trans), unused
-    uint64_t full[2];
-};
-
-struct LossLaunch {
-    LossSmemLayout lay;
-    unsigned int* done_counter;       // zeroed before the launch; the last CTA reduces the partial sums
-    float* loss_out;
-};
-
-__device__ __forceinline__ void layer_of(const LossParams& p, int gc, int& l) {
-    l = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxLossLayers; ++i)
-        if (i < p.n_layers && gc >= p.lv[i].chan_begin) l = i;
-}
-
-// sum over the CTA of three values, result in every thread; fixed order (warp tree, then a tree over the 32 warp
+// sum over the CTA of three values, result in every thread; fixed order (warp tree, then a tree over the warp
 // partials that every warp evaluates identically) -> deterministic.  One barrier.
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*red)[4]) {
 #pragma unroll
@@ -296,366 +278,439 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (
     }
 }
 
-__device__ void loss_finalize(const LossParams& p, float* __restrict__ loss_out, float (*red)[4]);
-
-__device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// One CTA of 1024 threads per SM.  Thread t owns the four consecutive loss-grid cells 4t .. 4t+3 (128-bit shared
-// loads / global stores); foreground pairs are walked one per thread.
-__global__ void __launch_bounds__(kLossThreads, 1) guidance_loss_kernel(const __grid_constant__ LossParams p,
-                                                                        const __grid_constant__ LossLaunch lp) {
-    extern __shared__ __align__(128) float lsm[];
-    __shared__ __align__(16) LossTables tb;
-    __shared__ unsigned int ticket;
-    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-    const int G = p.G, GG = G * G;
-    const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
-    const int n_pairs = pv.hdr->n_pairs;
-    int* const cnt = reinterpret_cast<int*>(lsm + lp.lay.cnt);
-    float* const gu = lsm + lp.lay.cnt;
-    float* const suc = lsm + lp.lay.uc;
-    float* const suo = lsm + lp.lay.uo;
-    float* const tmp = lsm + lp.lay.tmp;
-    float* const wo = lsm + lp.lay.wo;
-    float* const wt = lsm + lp.lay.wt;
-    float* const wrow = lsm + lp.lay.wrow;
-    float* const wcol = lsm + lp.lay.wcol;
-    uint2* const spairs = reinterpret_cast<uint2*>(lsm + lp.lay.pairs);
-    const bool pairs_in_smem = n_pairs <= lp.lay.pairs_cap;
-    const uint2* const pairs = pairs_in_smem ? spairs : pv.pairs;
-
-    if (tid == 0) {
-        mbar_init(&tb.full[0], 1);
-        mbar_init(&tb.full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (pairs_in_smem)
-        for (int i = tid; i < n_pairs; i += kLossThreads) spairs[i] = pv.pairs[i];
-    // per-thread constants: 4-bit masks of the own cells in the three background lists (multiplicities are 0/1 for
-    // lists that come from np.nonzero), and the box of the cells that are a source or a destination of a pair
-    uint32_t mo = 0, mt = 0, mc = 0;
-    bool binary = true;
-    int r0 = G, r1 = -1, s0 = G, s1 = -1;
-    const int q0 = 4 * tid;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int q = q0 + k;
-        if (q < GG) {
-            const ushort4 bc = pv.bgcnt[q];
-            mo |= (bc.x ? 1u : 0u) << k; mt |= (bc.y ? 1u : 0u) << k; mc |= (bc.z ? 1u : 0u) << k;
-            binary = binary && bc.x <= 1 && bc.y <= 1 && bc.z <= 1;
-            if (p.fg_kind && (pv.row_ptr[q + 1] > pv.row_ptr[q] || (bc.w & 1))) {
-                const int r = q / G, s = q - r * G;
-                r0 = min(r0, r); r1 = max(r1, r); s0 = min(s0, s); s1 = max(s1, s);
-            }
-        }
-    }
-    if (p.bg_kind == 2) { r0 = 0; r1 = G - 1; s0 = 0; s1 = G - 1; }      // local_avg needs up() on every background cell
-    {
-        r0 = __reduce_min_sync(0xFFFFFFFFu, r0); s0 = __reduce_min_sync(0xFFFFFFFFu, s0);
-        r1 = __reduce_max_sync(0xFFFFFFFFu, r1); s1 = __reduce_max_sync(0xFFFFFFFFu, s1);
-        const bool wbin = __all_sync(0xFFFFFFFFu, binary);
-        int* bx = tb.scratch;
-        if (lane == 0) { bx[wid * 8 + 0] = r0; bx[wid * 8 + 1] = r1; bx[wid * 8 + 2] = s0; bx[wid * 8 + 3] = s1; bx[wid * 8 + 4] = wbin ? 1 : 0; }
-        __syncthreads();
-        if (tid == 0) {
-            bool allbin = true;
-            for (int i = 0; i < kLossWarps; ++i) {
-                r0 = min(r0, bx[i * 8]); r1 = max(r1, bx[i * 8 + 1]); s0 = min(s0, bx[i * 8 + 2]); s1 = max(s1, bx[i * 8 + 3]);
-                allbin = allbin && bx[i * 8 + 4] != 0;
-            }
-            tb.box[0] = r0; tb.box[1] = r1; tb.box[2] = s0; tb.box[3] = s1;
-            tb.flags[0] = allbin ? 1 : 0;
-        }
-        __syncthreads();
-    }
-    if (tid < p.n_layers) {
-        const LossLayerDev& L = p.lv[tid];
-        tb.lconst[tid][0] = p.fg_kind ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
-        tb.lconst[tid][1] = p.bg_kind == 2 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
-        tb.lconst[tid][2] = p.bg_kind == 1 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
-        tb.lconst[tid][3] = 0.0f;
-    }
-    const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
-    __syncthreads();
-    const int br0 = tb.box[0], br1 = tb.box[1], bs0 = tb.box[2], bs1 = tb.box[3];
-    const bool any_box = br1 >= br0;
-    const bool bg_binary = tb.flags[0] != 0;
-    float fo[4], ft[4], fc[4];          // multiplicities of the own cells (general case: read once, kept in registers)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        fo[k] = (float)((mo >> k) & 1u); ft[k] = (float)((mt >> k) & 1u); fc[k] = (float)((mc >> k) & 1u);
-        if (!bg_binary && q0 + k < GG) {
-            const ushort4 bc = pv.bgcnt[q0 + k];
-            fo[k] = (float)bc.x; ft[k] = (float)bc.y; fc[k] = (float)bc.z;
-        }
-    }
-
-    auto issue = [&](int gc, int buf) {
-        int l;
-        layer_of(p, gc, l);
-        const LossLayerDev& L = p.lv[l];
-        const int hw = L.h * L.w;
-        const size_t off = (size_t)(gc - L.chan_begin) * hw;
-        float* st = lsm + lp.lay.stage + buf * lp.lay.stage_stride;
-        mbar_expect_tx(&tb.full[buf], 2u * hw * 4u);
-        tma_g2s(st, L.cur + off, hw * 4u, &tb.full[buf]);
-        tma_g2s(st + hw, L.orig + off, hw * 4u, &tb.full[buf]);
-    };
-
-    // foreground pairs, one per thread: the integer sign term goes to cnt[dst] with a shared-memory integer atomic -
-    // integer addition is associative, so the gradient does not depend on the order.
-    auto walk_pairs = [&](const float* uc, const float* uo, float& acc) {
-        for (int j = tid; j < n_pairs; j += kLossThreads) {
-            const uint2 e = pairs[j];
-            const int d = (int)(e.x >> 16);
-            const float df = uo[e.x & 0xFFFFu] - uc[d];
-            acc = fmaf((float)e.y, fabsf(df), acc);
-            if (df != 0.0f) atomicAdd(cnt + d, df > 0.0f ? -(int)e.y : (int)e.y);
-        }
-    };
-
-    int it = 0, cur_layer = -1;
-    if (tid == 0 && (int)blockIdx.x < p.total_channels) issue(blockIdx.x, 0);
-    for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int nxt = gc + gridDim.x;
-        if (tid == 0 && nxt < p.total_channels) issue(nxt, buf ^ 1);     // prefetch the next plane pair
-        int l;
-        layer_of(p, gc, l);
-        const LossLayerDev& L = p.lv[l];
-        const int c = gc - L.chan_begin;
-        const int h = L.h, w = L.w, hw = h * w;
-        const bool resize = (h != G) || (w != G);
-        const float* const pc_ = lsm + lp.lay.stage + buf * lp.lay.stage_stride;   // current plane, native resolution
-        const float* const po_ = pc_ + hw;                                          // recorded plane
-        if (q0 < GG) *reinterpret_cast<int4*>(cnt + q0) = make_int4(0, 0, 0, 0);
-        if (resize && l != cur_layer) {
-            // ---- per-layer tables (a CTA crosses a layer boundary at most n_layers times) ----
-            const float sy = (float)h / (float)G, sx = (float)w / (float)G;
-            if (tid < G) {
-                bilinear_tap(tid, h, sy, tb.ty0[tid], tb.ty1[tid], tb.tly[tid]);
-                bilinear_tap(tid, w, sx, tb.tx0[tid], tb.tx1[tid], tb.tlx[tid]);
-            }
-            __syncthreads();
-            if (tid < h) {       // up rows that touch native row tid, and their weights
-                int lo = G, hi = -1;
-                for (int r = 0; r < G; ++r)
-                    if (tb.ty0[r] == tid || tb.ty1[r] == tid) { lo = min(lo, r); hi = max(hi, r); }
-                hi = min(hi, lo + kWin - 1);
-                tb.ylo[tid] = lo; tb.yhi[tid] = hi;
-                for (int r = lo; r <= hi; ++r)
-                    wrow[tid * kWin + r - lo] = (tb.ty0[r] == tid ? 1.0f - tb.tly[r] : 0.0f) + (tb.ty1[r] == tid ? tb.tly[r] : 0.0f);
-            }
-            if (tid >= 64 && tid - 64 < w) {
-                const int j = tid - 64;
-                int lo = G, hi = -1;
-                for (int s = 0; s < G; ++s)
-                    if (tb.tx0[s] == j || tb.tx1[s] == j) { lo = min(lo, s); hi = max(hi, s); }
-                hi = min(hi, lo + kWin - 1);
-                tb.xlo[j] = lo; tb.xhi[j] = hi;
-                for (int s = lo; s <= hi; ++s)
-                    wcol[j * kWin + s - lo] = (tb.tx0[s] == j ? 1.0f - tb.tlx[s] : 0.0f) + (tb.tx1[s] == j ? tb.tlx[s] : 0.0f);
-            }
-            if (tid == 128) {
-                tb.box[4] = any_box ? tb.ty0[br0] : 0; tb.box[5] = any_box ? tb.ty1[br1] : -1;
-                tb.box[6] = any_box ? tb.tx0[bs0] : 0; tb.box[7] = any_box ? tb.tx1[bs1] : -1;
-            }
-            __syncthreads();
-            if (p.bg_kind == 1) {
-                // wo / wt = up^T applied to the background multiplicities (separable, via tmp)
-                for (int pass = 0; pass < 2; ++pass) {
-                    float* dst = pass == 0 ? wo : wt;
-                    for (int yi = wid; yi < h; yi += kLossWarps)
-                        for (int s = lane; s < G; s += 32) {
-                            float a = 0.0f;
-                            for (int r = tb.ylo[yi]; r <= tb.yhi[yi]; ++r) {
-                                const ushort4 bc = pv.bgcnt[r * G + s];
-                                a = fmaf(wrow[yi * kWin + r - tb.ylo[yi]], (float)(pass == 0 ? bc.x : bc.y), a);
-                            }
-                            tmp[yi * G + s] = a;
-                        }
-                    __syncthreads();
-                    for (int yi = wid; yi < h; yi += kLossWarps)
-                        for (int xj = lane; xj < w; xj += 32) {
-                            float a = 0.0f;
-                            for (int s = tb.xlo[xj]; s <= tb.xhi[xj]; ++s) a = fmaf(wcol[xj * kWin + s - tb.xlo[xj]], tmp[yi * G + s], a);
-                            dst[yi * w + xj] = a;
-                        }
-                    __syncthreads();
-                }
-            }
-        }
-        cur_layer = l;
-        mbar_wait(&tb.full[buf], (it >> 1) & 1);
-        __syncthreads();          // cnt is zero, the planes have landed
-        float acc_f = 0.0f, so = 0.0f, sc = 0.0f;
-        const float fscale = tb.lconst[l][0], lscale = tb.lconst[l][1], gscale = tb.lconst[l][2];
-        float* g = L.grad ? L.grad + (size_t)c * hw : nullptr;
-
-        if (!resize) {
-            // ================= layer already at the loss grid =================
-            if (p.fg_kind) walk_pairs(pc_, po_, acc_f);
-            float4 vc = make_float4(0, 0, 0, 0), vo = vc;
-            if (q0 < GG) {
-                vc = *reinterpret_cast<const float4*>(pc_ + q0);
-                vo = *reinterpret_cast<const float4*>(po_ + q0);
-            }
-            if (p.bg_kind == 1) {
-                so = fmaf(fo[0], vo.x, fmaf(fo[1], vo.y, fmaf(fo[2], vo.z, fo[3] * vo.w)));
-                sc = fmaf(ft[0], vc.x, fmaf(ft[1], vc.y, fmaf(ft[2], vc.z, ft[3] * vc.w)));
-            } else if (p.bg_kind == 2) {
-                so = fmaf(fc[0], fabsf(vo.x - vc.x), fmaf(fc[1], fabsf(vo.y - vc.y), fmaf(fc[2], fabsf(vo.z - vc.z), fc[3] * fabsf(vo.w - vc.w))));
-            }
-            float r0s = acc_f, r1s = so, r2s = sc;
-            block_sum3(r0s, r1s, r2s, tb.red);       // (its barrier also orders the cnt atomics)
-            float bg_term = 0.0f, bscale = 0.0f;
-            if (p.bg_kind == 1) {
-                const float delta = r1s * inv_no - r2s * inv_nt;
-                bg_term = fabsf(delta);
-                bscale = delta > 0.0f ? -gscale : (delta < 0.0f ? gscale : 0.0f);
-            } else if (p.bg_kind == 2) {
-                bg_term = r1s;
-            }
-            if (tid == 0) { p.partial[2 * gc] = r0s; p.partial[2 * gc + 1] = bg_term; }
-            if (g && q0 < GG) {
-                const int4 ci = *reinterpret_cast<const int4*>(cnt + q0);
-                float4 v = make_float4((float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale);
-                if (p.bg_kind == 1) {
-                    v.x = fmaf(ft[0], bscale, v.x); v.y = fmaf(ft[1], bscale, v.y); v.z = fmaf(ft[2], bscale, v.z); v.w = fmaf(ft[3], bscale, v.w);
-                } else if (p.bg_kind == 2) {
-                    const float dx = vo.x - vc.x, dy = vo.y - vc.y, dz = vo.z - vc.z, dw = vo.w - vc.w;
-                    v.x -= (float)((dx > 0.0f) - (dx < 0.0f)) * fc[0] * lscale; v.y -= (float)((dy > 0.0f) - (dy < 0.0f)) * fc[1] * lscale;
-                    v.z -= (float)((dz > 0.0f) - (dz < 0.0f)) * fc[2] * lscale; v.w -= (float)((dw > 0.0f) - (dw < 0.0f)) * fc[3] * lscale;
-                }
-                st_cs_f4(g + q0, v);
-            }
-        } else {
-            // ================= smaller layer: bilinear resize restricted to the active box =================
-            const int ny0 = tb.box[4], ny1 = tb.box[5], nx0 = tb.box[6], nx1 = tb.box[7];
-            for (int r = br0 + wid; r <= br1; r += kLossWarps) {
-                const int y0 = tb.ty0[r] * w, y1 = tb.ty1[r] * w;
-                const float ly = tb.tly[r], hy = 1.0f - ly;
-                for (int s = bs0 + lane; s <= bs1; s += 32) {
-                    const int x0 = tb.tx0[s], x1 = tb.tx1[s];
-                    const float lx = tb.tlx[s], hx = 1.0f - lx;
-                    suc[r * G + s] = hy * (hx * pc_[y0 + x0] + lx * pc_[y0 + x1]) + ly * (hx * pc_[y1 + x0] + lx * pc_[y1 + x1]);
-                    suo[r * G + s] = hy * (hx * po_[y0 + x0] + lx * po_[y0 + x1]) + ly * (hx * po_[y1 + x0] + lx * po_[y1 + x1]);
-                }
-            }
-            __syncthreads();
-            if (p.fg_kind) walk_pairs(suc, suo, acc_f);
-            float4 vc = make_float4(0, 0, 0, 0), vo = vc;
-            if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
-                for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(wo + i), b = *reinterpret_cast<const float4*>(po_ + i);
-                    const float4 e = *reinterpret_cast<const float4*>(wt + i), f = *reinterpret_cast<const float4*>(pc_ + i);
-                    so = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, so))));
-                    sc = fmaf(e.x, f.x, fmaf(e.y, f.y, fmaf(e.z, f.z, fmaf(e.w, f.w, sc))));
-                }
-            } else if (p.bg_kind == 2 && q0 < GG) {
-                vc = *reinterpret_cast<const float4*>(suc + q0);
-                vo = *reinterpret_cast<const float4*>(suo + q0);
-                so = fmaf(fc[0], fabsf(vo.x - vc.x), fmaf(fc[1], fabsf(vo.y - vc.y), fmaf(fc[2], fabsf(vo.z - vc.z), fc[3] * fabsf(vo.w - vc.w))));
-            }
-            float r0s = acc_f, r1s = so, r2s = sc;
-            block_sum3(r0s, r1s, r2s, tb.red);
-            float bg_term = 0.0f, bscale = 0.0f;
-            if (p.bg_kind == 1) {
-                const float delta = r1s * inv_no - r2s * inv_nt;
-                bg_term = fabsf(delta);
-                bscale = delta > 0.0f ? -gscale : (delta < 0.0f ? gscale : 0.0f);
-            } else if (p.bg_kind == 2) {
-                bg_term = r1s;
-            }
-            if (tid == 0) { p.partial[2 * gc] = r0s; p.partial[2 * gc + 1] = bg_term; }
-            if (g) {
-                // gradient w.r.t. up(cur) (zero outside the box), then the transposed resize in gather form
-                if (q0 < GG) {
-                    const int4 ci = *reinterpret_cast<const int4*>(cnt + q0);
-                    float4 v = make_float4((float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale);
-                    if (p.bg_kind == 2) {
-                        const float dx = vo.x - vc.x, dy = vo.y - vc.y, dz = vo.z - vc.z, dw = vo.w - vc.w;
-                        v.x -= (float)((dx > 0.0f) - (dx < 0.0f)) * fc[0] * lscale; v.y -= (float)((dy > 0.0f) - (dy < 0.0f)) * fc[1] * lscale;
-                        v.z -= (float)((dz > 0.0f) - (dz < 0.0f)) * fc[2] * lscale; v.w -= (float)((dw > 0.0f) - (dw < 0.0f)) * fc[3] * lscale;
-                    }
-                    *reinterpret_cast<float4*>(gu + q0) = v;      // own cells: integer read above, float written in place
-                }
-                __syncthreads();
-                for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
-                    const int lo = tb.ylo[yi];
-                    const int ra = max(lo, br0), rb = min(tb.yhi[yi], br1);
-                    for (int s = bs0 + lane; s <= bs1; s += 32) {
-                        float a = 0.0f;
-                        for (int r = ra; r <= rb; ++r) a = fmaf(wrow[yi * kWin + r - lo], gu[r * G + s], a);
-                        tmp[yi * G + s] = a;
-                    }
-                }
-                __syncthreads();
-                for (int yi = wid; yi < h; yi += kLossWarps) {
-                    const bool row_in = yi >= ny0 && yi <= ny1;
-                    for (int xj = lane; xj < w; xj += 32) {
-                        float a = 0.0f;
-                        if (row_in && xj >= nx0 && xj <= nx1) {
-                            const int lo = tb.xlo[xj];
-                            const int sa = max(lo, bs0), sb = min(tb.xhi[xj], bs1);
-                            for (int s = sa; s <= sb; ++s) a = fmaf(wcol[xj * kWin + s - lo], tmp[yi * G + s], a);
-                        }
-                        if (p.bg_kind == 1) a = fmaf(bscale, wt[yi * w + xj], a);
-                        g[yi * w + xj] = a;
-                    }
-                }
-            }
-        }
-        __syncthreads();     // every read of the stage / cnt / uc / tmp is done before the next iteration reuses them
-    }
-    // ---- the last CTA to finish reduces the per-channel partial sums (fixed order) ----
-    __threadfence();
-    if (tid == 0) ticket = atomicAdd(lp.done_counter, 1u);
-    __syncthreads();
-    if (ticket == gridDim.x - 1) {
-        __threadfence();
-        loss_finalize(p, lp.loss_out, tb.red);
-    }
-}
-
-__device__ __forceinline__ float block_sum_256(float v, float* sm) {
+__device__ __forceinline__ float block_sum1(float v, float* sm) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     if (lane_id() == 0) sm[warp_id()] = v;
     __syncthreads();
-    float t = lane_id() < (int)(blockDim.x >> 5) ? sm[lane_id()] : 0.0f;
+    float t = lane_id() < kLossWarps ? sm[lane_id()] : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
     __syncthreads();
     return t;
 }
 
-// Fixed-order reduction of the per-channel partials -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l.
-__device__ void loss_finalize(const LossParams& p, float* __restrict__ loss_out, float (*red)[4]) {
-    float* sm = &red[0][0];      // kLossWarps * 4 floats >= 32
+// Called by every CTA of both kernels when it is done; the last one reduces the per-channel partials in a fixed
+// order -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l.
+__device__ void loss_finish(const LossParams& p, const LossFinal& f, float* red32) {
+    __shared__ unsigned int ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(f.done_counter, 1u);
+    __syncthreads();
+    if (ticket != f.total_ctas - 1) return;
+    __threadfence();
     float total = 0.0f;
-    for (int l = 0; l < p.n_layers; ++l) {
-        const LossLayerDev& L = p.lv[l];
+    for (int l = 0; l < f.n_layers; ++l) {
         float a = 0.0f, b = 0.0f;
-        for (int c = threadIdx.x; c < L.C; c += blockDim.x) {
-            a += __ldcg(p.partial + 2 * (L.chan_begin + c));
-            b += __ldcg(p.partial + 2 * (L.chan_begin + c) + 1);
+        for (int c = threadIdx.x; c < f.C[l]; c += blockDim.x) {
+            a += __ldcg(p.partial + 2 * (f.partial_begin[l] + c));
+            b += __ldcg(p.partial + 2 * (f.partial_begin[l] + c) + 1);
         }
-        a = block_sum_256(a, sm);
-        b = block_sum_256(b, sm);
-        const float fg = p.fg_kind ? a / (float)p.n_fg / (float)L.C : 0.0f;
-        const float bg = p.bg_kind == 2 ? b / (float)p.n_bg_common / (float)L.C : (p.bg_kind == 1 ? b / (float)L.C : 0.0f);
-        if (threadIdx.x == 0) {
-            loss_out[1 + 2 * l] = fg;
-            loss_out[2 + 2 * l] = bg;
-        }
-        if (p.fg_kind) total += L.fgw * fg;
-        if (p.bg_kind) total += L.bgw * bg;
+        a = block_sum1(a, red32);
+        b = block_sum1(b, red32);
+        const float fg = p.fg_kind ? a / (float)p.n_fg / (float)f.C[l] : 0.0f;
+        const float bg = p.bg_kind == 2 ? b / (float)p.n_bg_common / (float)f.C[l] : (p.bg_kind == 1 ? b / (float)f.C[l] : 0.0f);
+        if (threadIdx.x == 0) { f.loss_out[1 + 2 * l] = fg; f.loss_out[2 + 2 * l] = bg; }
+        if (p.fg_kind) total += f.fgw[l] * fg;
+        if (p.bg_kind) total += f.bgw[l] * bg;
     }
-    if (threadIdx.x == 0) loss_out[0] = total;
+    if (threadIdx.x == 0) f.loss_out[0] = total;
+}
+
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float sgn(float d) { return d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f); }
+
+// ---- layers at the loss-grid resolution -------------------------------------------------------------
+template <bool kBinary>
+__global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid_constant__ LossParams p,
+                                                                    const __grid_constant__ LossFinal fin) {
+    __shared__ __align__(16) int cnt[kMaxG * kMaxG];
+    __shared__ __align__(16) float red[kLossWarps][4];
+    __shared__ float red32[32];
+    __shared__ float lconst[kMaxLossLayers][4];
+    const int tid = threadIdx.x;
+    const int GG = p.G * p.G;
+    const PlanView pv = plan_view(const_cast<void*>(p.plan), p.G, p.plan_cap);
+    const int n_pairs = pv.hdr->n_pairs;
+    const uint2* __restrict__ pairs = pv.pairs;
+    // membership of the own cells in the three background lists as 16-bit masks (bit 4k+i = cell i of group k).
+    // Lists that come from np.nonzero never repeat a cell; if a generic caller does, the multiplicities are re-read
+    // from the plan in the (slower) general path.
+    uint32_t mo = 0, mt = 0, mc = 0;
+#pragma unroll
+    for (int k = 0; k < kOwnGroups; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = 4 * (tid + k * kLossThreads) + i;
+            if (q < GG) {
+                const ushort4 bc = pv.bgcnt[q];
+                mo |= (bc.x ? 1u : 0u) << (4 * k + i); mt |= (bc.y ? 1u : 0u) << (4 * k + i); mc |= (bc.z ? 1u : 0u) << (4 * k + i);
+            }
+        }
+    auto wgt = [&](uint32_t mask, int k, int i, int which) -> float {     // multiplicity of own cell (k, i) in list `which`
+        if (kBinary) return (float)((mask >> (4 * k + i)) & 1u);
+        const ushort4 bc = pv.bgcnt[4 * (tid + k * kLossThreads) + i];
+        return (float)(which == 0 ? bc.x : which == 1 ? bc.y : bc.z);
+    };
+    if (tid < p.n_layers) {
+        const LossLayerDev& L = p.lv[tid];
+        lconst[tid][0] = p.fg_kind ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
+        lconst[tid][1] = p.bg_kind == 2 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
+        lconst[tid][2] = p.bg_kind == 1 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
+    }
+    const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
+    __syncthreads();
+
+    for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x) {
+        const int l = layer_of(p, gc);
+        const LossLayerDev& L = p.lv[l];
+        const int c = gc - L.chan_begin;
+        const float* __restrict__ cur = L.cur + (size_t)c * GG;
+        const float* __restrict__ org = L.orig + (size_t)c * GG;
+        float4 vc[kOwnGroups], vo[kOwnGroups];
+#pragma unroll
+        for (int k = 0; k < kOwnGroups; ++k) {
+            const int q = 4 * (tid + k * kLossThreads);
+            vc[k] = vo[k] = make_float4(0, 0, 0, 0);
+            if (q < GG) {
+                vc[k] = __ldg(reinterpret_cast<const float4*>(cur + q));
+                vo[k] = __ldg(reinterpret_cast<const float4*>(org + q));
+                *reinterpret_cast<int4*>(cnt + q) = make_int4(0, 0, 0, 0);
+            }
+        }
+        __syncthreads();
+        float acc_f = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        if (p.fg_kind) {
+            // four independent pair chains per thread and iteration (memory-level parallelism for the L1 gathers)
+            for (int j0 = tid; j0 < n_pairs; j0 += 4 * kLossThreads) {
+                uint2 e[4];
+                float df[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * kLossThreads;
+                    e[u] = j < n_pairs ? pairs[j] : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) df[u] = __ldg(org + (e[u].x & 0xFFFFu)) - __ldg(cur + (e[u].x >> 16));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc_f = fmaf((float)e[u].y, fabsf(df[u]), acc_f);
+                    if (df[u] != 0.0f && e[u].y) atomicAdd(cnt + (e[u].x >> 16), df[u] > 0.0f ? -(int)e[u].y : (int)e[u].y);
+                }
+            }
+        }
+        if (p.bg_kind == 1) {
+#pragma unroll
+            for (int k = 0; k < kOwnGroups; ++k) {
+                if (4 * (tid + k * kLossThreads) >= GG) break;
+                s1 = fmaf(wgt(mo, k, 0, 0), vo[k].x, fmaf(wgt(mo, k, 1, 0), vo[k].y, fmaf(wgt(mo, k, 2, 0), vo[k].z, fmaf(wgt(mo, k, 3, 0), vo[k].w, s1))));
+                s2 = fmaf(wgt(mt, k, 0, 1), vc[k].x, fmaf(wgt(mt, k, 1, 1), vc[k].y, fmaf(wgt(mt, k, 2, 1), vc[k].z, fmaf(wgt(mt, k, 3, 1), vc[k].w, s2))));
+            }
+        } else if (p.bg_kind == 2) {
+#pragma unroll
+            for (int k = 0; k < kOwnGroups; ++k) {
+                if (4 * (tid + k * kLossThreads) >= GG) break;
+                s1 = fmaf(wgt(mc, k, 0, 2), fabsf(vo[k].x - vc[k].x), fmaf(wgt(mc, k, 1, 2), fabsf(vo[k].y - vc[k].y),
+                     fmaf(wgt(mc, k, 2, 2), fabsf(vo[k].z - vc[k].z), fmaf(wgt(mc, k, 3, 2), fabsf(vo[k].w - vc[k].w), s1))));
+            }
+        }
+        block_sum3(acc_f, s1, s2, red);       // (its barrier also orders the cnt atomics)
+        const float fscale = lconst[l][0], lscale = lconst[l][1], gscale = lconst[l][2];
+        float bg_term = 0.0f, bscale = 0.0f;
+        if (p.bg_kind == 1) {
+            const float delta = s1 * inv_no - s2 * inv_nt;
+            bg_term = fabsf(delta);
+            bscale = -sgn(delta) * gscale;
+        } else if (p.bg_kind == 2) {
+            bg_term = s1;
+        }
+        if (tid == 0) { p.partial[2 * (L.partial_begin + c)] = acc_f; p.partial[2 * (L.partial_begin + c) + 1] = bg_term; }
+        if (L.grad) {
+            float* g = L.grad + (size_t)c * GG;
+#pragma unroll
+            for (int k = 0; k < kOwnGroups; ++k) {
+                const int q = 4 * (tid + k * kLossThreads);
+                if (q >= GG) break;
+                const int4 ci = *reinterpret_cast<const int4*>(cnt + q);
+                float4 v = make_float4((float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale);
+                if (p.bg_kind == 1) {
+                    v.x = fmaf(wgt(mt, k, 0, 1), bscale, v.x); v.y = fmaf(wgt(mt, k, 1, 1), bscale, v.y);
+                    v.z = fmaf(wgt(mt, k, 2, 1), bscale, v.z); v.w = fmaf(wgt(mt, k, 3, 1), bscale, v.w);
+                } else if (p.bg_kind == 2) {
+                    v.x -= sgn(vo[k].x - vc[k].x) * wgt(mc, k, 0, 2) * lscale; v.y -= sgn(vo[k].y - vc[k].y) * wgt(mc, k, 1, 2) * lscale;
+                    v.z -= sgn(vo[k].z - vc[k].z) * wgt(mc, k, 2, 2) * lscale; v.w -= sgn(vo[k].w - vc[k].w) * wgt(mc, k, 3, 2) * lscale;
+                }
+                st_cs_f4(g + q, v);
+            }
+        }
+        __syncthreads();     // cnt / red are reused by the next channel
+    }
+    loss_finish(p, fin, red32);
+}
+
+// ---- layers smaller than the loss grid -----------------------------------------------------------------
+// Per-layer tables, built once per evaluation by loss_resize_setup_kernel (one CTA per resized layer) in global
+// memory and copied to shared memory by every CTA of loss_resize_kernel:
+//   bilinear taps of every up row / column, the up rows (columns) that touch each native row (column) with their
+//   weights (the transposed resize in gather form), up^T(background multiplicities) at native resolution, and the
+//   native box that the active up box touches.
+struct LayerTabSmall {
+    int ty0[kMaxG], ty1[kMaxG], tx0[kMaxG], tx1[kMaxG];
+    float tly[kMaxG], tlx[kMaxG];
+    int ylo[kMaxNative], yhi[kMaxNative], xlo[kMaxNative], xhi[kMaxNative];
+    float wrow[kMaxNative * kWin], wcol[kMaxNative * kWin];
+    int box[8];                        // up space: r0, r1, s0, s1; native: y0, y1, x0, x1
+};
+struct LayerTab : LayerTabSmall {
+    float wo[kMaxNative * kMaxNative], wt[kMaxNative * kMaxNative];
+};
+static_assert(sizeof(LayerTabSmall) % 16 == 0 && sizeof(LayerTab) % 16 == 0, "tables are copied with 128-bit accesses");
+
+struct SetupParams {
+    const void* plan;
+    int plan_cap, G, h, w, fg_kind, bg_kind;
+};
+
+__global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_constant__ SetupParams p, LayerTab* __restrict__ tabs) {
+    __shared__ float tmp[kMaxNative * kMaxG];
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    LayerTab& T = tabs[0];
+    const int G = p.G, h = p.h, w = p.w;
+    const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
+    const float sy = (float)h / (float)G, sx = (float)w / (float)G;
+    if (tid < G) {
+        bilinear_tap(tid, h, sy, T.ty0[tid], T.ty1[tid], T.tly[tid]);
+        bilinear_tap(tid, w, sx, T.tx0[tid], T.tx1[tid], T.tlx[tid]);
+    }
+    __syncthreads();
+    if (tid < h) {       // up rows that touch native row tid, and their weights
+        int lo = G, hi = -1;
+        for (int r = 0; r < G; ++r)
+            if (T.ty0[r] == tid || T.ty1[r] == tid) { lo = min(lo, r); hi = max(hi, r); }
+        hi = min(hi, lo + kWin - 1);
+        T.ylo[tid] = lo; T.yhi[tid] = hi;
+        for (int r = lo; r <= hi; ++r)
+            T.wrow[tid * kWin + r - lo] = (T.ty0[r] == tid ? 1.0f - T.tly[r] : 0.0f) + (T.ty1[r] == tid ? T.tly[r] : 0.0f);
+    }
+    if (tid >= 64 && tid - 64 < w) {
+        const int j = tid - 64;
+        int lo = G, hi = -1;
+        for (int s = 0; s < G; ++s)
+            if (T.tx0[s] == j || T.tx1[s] == j) { lo = min(lo, s); hi = max(hi, s); }
+        hi = min(hi, lo + kWin - 1);
+        T.xlo[j] = lo; T.xhi[j] = hi;
+        for (int s = lo; s <= hi; ++s)
+            T.wcol[j * kWin + s - lo] = (T.tx0[s] == j ? 1.0f - T.tlx[s] : 0.0f) + (T.tx1[s] == j ? T.tlx[s] : 0.0f);
+    }
+    if (tid == 128) {
+        const bool full = p.bg_kind == 2;      // local_avg needs up() on every background cell
+        const bool none = !p.fg_kind && !full;
+        const int r0 = full ? 0 : (none ? G : pv.hdr->box_r0), r1 = full ? G - 1 : (none ? -1 : pv.hdr->box_r1);
+        const int s0 = full ? 0 : (none ? G : pv.hdr->box_s0), s1 = full ? G - 1 : (none ? -1 : pv.hdr->box_s1);
+        const bool any = r1 >= r0;
+        T.box[0] = r0; T.box[1] = r1; T.box[2] = s0; T.box[3] = s1;
+        T.box[4] = any ? T.ty0[r0] : 0; T.box[5] = any ? T.ty1[r1] : -1;
+        T.box[6] = any ? T.tx0[s0] : 0; T.box[7] = any ? T.tx1[s1] : -1;
+    }
+    __syncthreads();
+    // wo / wt = up^T applied to the background multiplicities (separable, via tmp)
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? T.wo : T.wt;
+        for (int yi = wid; yi < h; yi += 8)
+            for (int s = lane; s < G; s += 32) {
+                float a = 0.0f;
+                for (int r = T.ylo[yi]; r <= T.yhi[yi]; ++r) {
+                    const ushort4 bc = pv.bgcnt[r * G + s];
+                    a = fmaf(T.wrow[yi * kWin + r - T.ylo[yi]], (float)(pass == 0 ? bc.x : bc.y), a);
+                }
+                tmp[yi * G + s] = a;
+            }
+        __syncthreads();
+        for (int yi = wid; yi < h; yi += 8)
+            for (int xj = lane; xj < w; xj += 32) {
+                float a = 0.0f;
+                for (int s = T.xlo[xj]; s <= T.xhi[xj]; ++s) a = fmaf(T.wcol[xj * kWin + s - T.xlo[xj]], tmp[yi * G + s], a);
+                dst[yi * w + xj] = a;
+            }
+        __syncthreads();
+    }
+}
+
+struct ResizeShared {
+    float red[kLossWarps][4];
+    float red32[32];
+    float lconst[kMaxLossLayers][4];
+};
+
+// kG = 64: the loss grid of the reference (shifts instead of integer divisions); kG = 0: any grid <= 64.
+template <int kG>
+__global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __grid_constant__ LossParams p,
+                                                                      const __grid_constant__ LossFinal fin,
+                                                                      const __grid_constant__ ResizeLayout lay) {
+    extern __shared__ __align__(16) float rsm[];
+    __shared__ __align__(16) ResizeShared sh;
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const int G = kG ? kG : p.G, GG = G * G;
+    const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
+    const int n_pairs = pv.hdr->n_pairs;
+    const uint2* __restrict__ pairs = pv.pairs;
+    LayerTabSmall& T = *reinterpret_cast<LayerTabSmall*>(rsm + lay.tab);
+    float* const two = rsm + lay.wo;           // up^T(background multiplicities) of the current layer
+    float* const twt = rsm + lay.wt;
+    float* const planes = rsm + lay.planes;
+    float* const suc = rsm + lay.uc;          // box-local: index (r - br0) * bw + (s - bs0)
+    float* const suo = rsm + lay.uo;
+    int* const cnt = reinterpret_cast<int*>(rsm + lay.cnt);
+    float* const gu = rsm + lay.cnt;
+    float* const tmp = rsm + lay.tmp;
+
+    if (tid < p.n_layers) {
+        const LossLayerDev& L = p.lv[tid];
+        sh.lconst[tid][0] = p.fg_kind ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
+        sh.lconst[tid][1] = p.bg_kind == 2 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
+        sh.lconst[tid][2] = p.bg_kind == 1 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
+    }
+    const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
+    // the active box is a property of the plan (identical in every layer's table)
+    const LayerTab* tab0 = static_cast<const LayerTab*>(p.lv[0].tab);
+    const int br0 = tab0->box[0], br1 = tab0->box[1], bs0 = tab0->box[2], bs1 = tab0->box[3];
+    const bool any_box = br1 >= br0;
+    const int bw = any_box ? bs1 - bs0 + 1 : 0, bh = any_box ? br1 - br0 + 1 : 0;
+    const int bcells = bw * bh;
+    __syncthreads();
+    if (bcells > lay.box_cap) {      // the caller under-sized the box-local buffers: poison the result instead of corrupting memory
+        for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x)
+            if (tid == 0) {
+                const int l = layer_of(p, gc);
+                p.partial[2 * (p.lv[l].partial_begin + gc - p.lv[l].chan_begin)] = __int_as_float(0x7FC00000);
+                p.partial[2 * (p.lv[l].partial_begin + gc - p.lv[l].chan_begin) + 1] = __int_as_float(0x7FC00000);
+            }
+        loss_finish(p, fin, sh.red32);
+        return;
+    }
+
+    int cur_layer = -1;
+    for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x) {
+        const int l = layer_of(p, gc);
+        const LossLayerDev& L = p.lv[l];
+        const int c = gc - L.chan_begin;
+        const int h = L.h, w = L.w, hw = h * w;
+        float* const pc_ = planes;
+        float* const po_ = planes + hw;
+        {   // stage both planes (coalesced 128-bit loads)
+            const float4* c4 = reinterpret_cast<const float4*>(L.cur + (size_t)c * hw);
+            const float4* o4 = reinterpret_cast<const float4*>(L.orig + (size_t)c * hw);
+            for (int i = tid; i < hw / 4; i += kLossThreads) {
+                reinterpret_cast<float4*>(pc_)[i] = __ldg(c4 + i);
+                reinterpret_cast<float4*>(po_)[i] = __ldg(o4 + i);
+            }
+            for (int i = tid; i < bcells; i += kLossThreads) cnt[i] = 0;
+        }
+        if (l != cur_layer) {       // (a CTA crosses a layer boundary at most n_layers times)
+            const LayerTab* tl = static_cast<const LayerTab*>(L.tab);
+            const float4* src = reinterpret_cast<const float4*>(static_cast<const LayerTabSmall*>(tl));
+            float4* dst = reinterpret_cast<float4*>(&T);
+            for (int i = tid; i < (int)(sizeof(LayerTabSmall) / 16); i += kLossThreads) dst[i] = src[i];
+            if (p.bg_kind == 1)
+                for (int i = tid; i < hw / 4; i += kLossThreads) {
+                    reinterpret_cast<float4*>(two)[i] = reinterpret_cast<const float4*>(tl->wo)[i];
+                    reinterpret_cast<float4*>(twt)[i] = reinterpret_cast<const float4*>(tl->wt)[i];
+                }
+            cur_layer = l;
+        }
+        __syncthreads();          // planes staged, cnt zeroed, tables loaded
+        const int ny0 = T.box[4], ny1 = T.box[5], nx0 = T.box[6], nx1 = T.box[7];
+        // up(cur), up(orig) inside the box
+        for (int r = br0 + wid; r <= br1; r += kLossWarps) {
+            const int y0 = T.ty0[r] * w, y1 = T.ty1[r] * w;
+            const float ly = T.tly[r], hy = 1.0f - ly;
+            for (int s = bs0 + lane; s <= bs1; s += 32) {
+                const int x0 = T.tx0[s], x1 = T.tx1[s];
+                const float lx = T.tlx[s], hx = 1.0f - lx;
+                const int b = (r - br0) * bw + (s - bs0);
+                suc[b] = hy * (hx * pc_[y0 + x0] + lx * pc_[y0 + x1]) + ly * (hx * pc_[y1 + x0] + lx * pc_[y1 + x1]);
+                suo[b] = hy * (hx * po_[y0 + x0] + lx * po_[y0 + x1]) + ly * (hx * po_[y1 + x0] + lx * po_[y1 + x1]);
+            }
+        }
+        __syncthreads();
+        float acc_f = 0.0f, s1s = 0.0f, s2s = 0.0f;
+        if (p.fg_kind) {
+            const int boff = br0 * bw + bs0;
+            for (int j = tid; j < n_pairs; j += kLossThreads) {
+                const uint2 e = pairs[j];
+                const int d = (int)(e.x >> 16), sc_ = (int)(e.x & 0xFFFFu);
+                const int dr = kG ? d >> 6 : d / G, sr = kG ? sc_ >> 6 : sc_ / G;
+                const int db = dr * bw + (d - dr * G) - boff, sb = sr * bw + (sc_ - sr * G) - boff;
+                const float df = suo[sb] - suc[db];
+                acc_f = fmaf((float)e.y, fabsf(df), acc_f);
+                if (df != 0.0f) atomicAdd(cnt + db, df > 0.0f ? -(int)e.y : (int)e.y);
+            }
+        }
+        const float fscale = sh.lconst[l][0], lscale = sh.lconst[l][1], gscale = sh.lconst[l][2];
+        if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
+            for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
+                const float4 a = *reinterpret_cast<const float4*>(two + i), b = *reinterpret_cast<const float4*>(po_ + i);
+                const float4 e = *reinterpret_cast<const float4*>(twt + i), f = *reinterpret_cast<const float4*>(pc_ + i);
+                s1s = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s1s))));
+                s2s = fmaf(e.x, f.x, fmaf(e.y, f.y, fmaf(e.z, f.z, fmaf(e.w, f.w, s2s))));
+            }
+        } else if (p.bg_kind == 2) {       // box = whole grid
+            for (int q = tid; q < GG; q += kLossThreads) s1s = fmaf((float)pv.bgcnt[q].z, fabsf(suo[q] - suc[q]), s1s);
+        }
+        block_sum3(acc_f, s1s, s2s, sh.red);
+        float bg_term = 0.0f, bscale = 0.0f;
+        if (p.bg_kind == 1) {
+            const float delta = s1s * inv_no - s2s * inv_nt;
+            bg_term = fabsf(delta);
+            bscale = -sgn(delta) * gscale;
+        } else if (p.bg_kind == 2) {
+            bg_term = s1s;
+        }
+        if (tid == 0) { p.partial[2 * (L.partial_begin + c)] = acc_f; p.partial[2 * (L.partial_begin + c) + 1] = bg_term; }
+        if (L.grad) {
+            float* g = L.grad + (size_t)c * hw;
+            // gradient w.r.t. up(cur) inside the box (in place: integer -> float), then up^T in gather form
+            for (int i = tid; i < bcells; i += kLossThreads) {
+                float v = (float)cnt[i] * fscale;
+                if (p.bg_kind == 2) v -= sgn(suo[i] - suc[i]) * (float)pv.bgcnt[i].z * lscale;
+                gu[i] = v;
+            }
+            __syncthreads();
+            for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
+                const int lo = T.ylo[yi];
+                const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
+                const float* wr = T.wrow + yi * kWin - lo;
+                for (int s = bs0 + lane; s <= bs1; s += 32) {
+                    float a = 0.0f;
+                    const float* gp = gu + (s - bs0) - br0 * bw;
+                    for (int r = ra; r <= rb; ++r) a = fmaf(wr[r], gp[r * bw], a);
+                    tmp[yi * G + s] = a;
+                }
+            }
+            __syncthreads();
+            for (int yi = wid; yi < h; yi += kLossWarps) {
+                const bool row_in = yi >= ny0 && yi <= ny1;
+                for (int xj = lane; xj < w; xj += 32) {
+                    float a = 0.0f;
+                    if (row_in && xj >= nx0 && xj <= nx1) {
+                        const int lo = T.xlo[xj];
+                        const int sa = max(lo, bs0), sb = min(T.xhi[xj], bs1);
+                        const float* wc = T.wcol + xj * kWin - lo;
+                        const float* tp = tmp + yi * G;
+                        for (int s = sa; s <= sb; ++s) a = fmaf(wc[s], tp[s], a);
+                    }
+                    if (p.bg_kind == 1) a = fmaf(bscale, twt[yi * w + xj], a);
+                    g[yi * w + xj] = a;
+                }
+            }
+        }
+        __syncthreads();     // planes / cnt / uc / tmp are reused by the next channel
+    }
+    loss_finish(p, fin, sh.red32);
 }
 
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, size_t n, const float* __restrict__ scale) {
@@ -705,85 +760,143 @@ int dh_build_loss_plan(const int32_t* fg_src, const int32_t* fg_dst, int n_fg, c
     return DH_OK;
 }
 
+static size_t loss_ws_layout(size_t channels, size_t* o_counter) {
+    size_t o = (sizeof(float) * 2 * channels + 15) / 16 * 16;
+    *o_counter = o; o += 16;
+    return o;
+}
+
 size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels) {
     if (n_layers < 1 || max_channels < 1) return 0;
-    return sizeof(float) * 2 * (size_t)n_layers * max_channels + 16;
+    size_t a;
+    return loss_ws_layout((size_t)n_layers * max_channels, &a);
+}
+
+size_t dh_loss_resize_tables_bytes(void) { return sizeof(LayerTab); }
+
+int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int w, int fg_kind, int bg_kind, void* tables,
+                                void* stream) {
+    DH_REQUIRE(plan && tables && grid >= 1 && grid <= kMaxG && h >= 1 && w >= 1 && n_fg >= 0);
+    if (h > grid || w > grid || h > kMaxNative || w > kMaxNative) return DH_ERR_UNSUPPORTED;
+    if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
+    SetupParams sp;
+    sp.plan = plan; sp.plan_cap = n_fg; sp.G = grid; sp.h = h; sp.w = w; sp.fg_kind = fg_kind; sp.bg_kind = bg_kind;
+    loss_resize_setup_kernel<<<1, 256, 0, as_stream(stream)>>>(sp, static_cast<LayerTab*>(tables));
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
+int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags) {
+    DH_REQUIRE(plan_header_host);
+    const PlanHeader* h = static_cast<const PlanHeader*>(plan_header_host);
+    if (n_pairs) *n_pairs = h->n_pairs;
+    if (plan_flags) *plan_flags = h->reserved & 1;
+    if (box_cells) *box_cells = h->box_r1 >= h->box_r0 ? (h->box_r1 - h->box_r0 + 1) * (h->box_s1 - h->box_s0 + 1) : 0;
+    return DH_OK;
 }
 
 int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan, int n_fg, int n_bg_orig,
-                     int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind, float* loss_out, void* ws, size_t ws_bytes,
-                     void* stream) {
+                     int n_bg_trans, int n_bg_common, int box_cells, int plan_flags, int fg_kind, int bg_kind, float* loss_out,
+                     void* ws, size_t ws_bytes, void* stream) {
     DH_REQUIRE(layers_host && n_layers >= 1 && n_layers <= kMaxLossLayers && loss_out && ws && plan);
     DH_REQUIRE(grid >= 1 && grid <= kMaxG);
     DH_REQUIRE(n_fg >= 0 && n_bg_orig >= 0 && n_bg_trans >= 0 && n_bg_common >= 0);
     if (bg_kind != 0 && bg_kind != 1 && bg_kind != 2) return DH_ERR_INVALID_ARGUMENT;
     if (fg_kind != 0 && fg_kind != 1) return DH_ERR_INVALID_ARGUMENT;
-    LossParams p;
-    memset(&p, 0, sizeof(p));
-    int chan = 0, hw_max = 0, hw_r = 0, h_r = 0;
+    LossParams pf, pr;      // flat (native == grid) and resized layers
+    LossFinal fin;
+    memset(&pf, 0, sizeof(pf));
+    memset(&pr, 0, sizeof(pr));
+    memset(&fin, 0, sizeof(fin));
+    int chan = 0, hw_r = 0, h_r = 0;
     for (int i = 0; i < n_layers; ++i) {
         const dh_loss_layer& s = layers_host[i];
         DH_REQUIRE(s.cur && s.orig && s.channels >= 1 && s.h >= 1 && s.w >= 1);
-        if (s.h > kMaxNative || s.w > kMaxNative) return DH_ERR_UNSUPPORTED;
-        if (((size_t)s.h * s.w) % 4 != 0) return DH_ERR_UNSUPPORTED;     // TMA bulk copies move multiples of 16 bytes
+        if (s.h > kMaxNative || s.w > kMaxNative || s.h > grid || s.w > grid) return DH_ERR_UNSUPPORTED;
+        if (((size_t)s.h * s.w) % 4 != 0) return DH_ERR_UNSUPPORTED;     // 128-bit plane loads
         if ((reinterpret_cast<uintptr_t>(s.cur) & 15) || (reinterpret_cast<uintptr_t>(s.orig) & 15) ||
             (s.grad && (reinterpret_cast<uintptr_t>(s.grad) & 15)))
             return DH_ERR_INVALID_ARGUMENT;
-        LossLayerDev& L = p.lv[i];
+        const bool flat = s.h == grid && s.w == grid;
+        if (flat && (grid * grid) % 4 != 0) return DH_ERR_UNSUPPORTED;
+        if (!flat && (!s.resize_tables || (reinterpret_cast<uintptr_t>(s.resize_tables) & 15))) return DH_ERR_INVALID_ARGUMENT;
+        LossParams& q = flat ? pf : pr;
+        LossLayerDev& L = q.lv[q.n_layers++];
         L.cur = s.cur; L.orig = s.orig; L.grad = s.grad;
         L.C = s.channels; L.h = s.h; L.w = s.w; L.fgw = s.fg_weight; L.bgw = s.bg_weight;
-        L.chan_begin = chan;
+        L.tab = flat ? nullptr : s.resize_tables;
+        L.chan_begin = q.total_channels;
+        L.partial_begin = chan;
+        q.total_channels += s.channels;
+        fin.C[i] = s.channels; fin.partial_begin[i] = chan; fin.fgw[i] = s.fg_weight; fin.bgw[i] = s.bg_weight;
         chan += s.channels;
-        const int hw = s.h * s.w;
-        if (hw > hw_max) hw_max = hw;
-        if (s.h != grid || s.w != grid) {
-            if (hw > hw_r) hw_r = hw;
+        if (!flat) {
+            if (s.h * s.w > hw_r) hw_r = s.h * s.w;
             if (s.h > h_r) h_r = s.h;
         }
     }
-    const size_t partial_bytes = sizeof(float) * 2 * (size_t)chan;
-    if (ws_bytes < partial_bytes + 16) return DH_ERR_WORKSPACE;
-    p.n_layers = n_layers; p.total_channels = chan; p.G = grid;
-    p.plan = plan; p.plan_cap = n_fg;
-    p.n_fg = n_fg; p.n_bg_orig = n_bg_orig; p.n_bg_trans = n_bg_trans; p.n_bg_common = n_bg_common;
-    p.fg_kind = fg_kind; p.bg_kind = bg_kind;
-    p.partial = static_cast<float*>(ws);
-    LossLaunch lp;
-    const int GG = grid * grid;
-    auto up4 = [](int v) { return (v + 3) / 4 * 4; };
-    int o = 0;
-    lp.lay.stage = o; lp.lay.stage_stride = up4(2 * hw_max); o += 2 * lp.lay.stage_stride;
-    lp.lay.cnt = o;   o += up4(GG);
-    lp.lay.uc = o;    if (hw_r) o += up4(GG);
-    lp.lay.uo = o;    if (hw_r) o += up4(GG);
-    lp.lay.tmp = o;   if (hw_r) o += up4(h_r * grid);
-    lp.lay.wo = o;    if (hw_r) o += up4(hw_r);
-    lp.lay.wt = o;    if (hw_r) o += up4(hw_r);
-    lp.lay.wrow = o;  if (hw_r) o += kMaxNative * kWin;
-    lp.lay.wcol = o;  if (hw_r) o += kMaxNative * kWin;
-    // whatever is left of the 227 KB goes to the pair list (8 bytes per entry); larger lists are read from global memory
-    lp.lay.pairs = o;
-    const int max_floats = (227 * 1024 - 8192) / 4;     // static tables + alignment slack
-    int cap = (max_floats - o) / 2;
-    if (cap > n_fg) cap = n_fg;
-    if (cap < 0) cap = 0;
-    lp.lay.pairs_cap = cap;
-    o += up4(2 * cap);
-    lp.lay.total_floats = o;
-    lp.done_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + (partial_bytes + 15) / 16 * 16);
-    if (ws_bytes < (partial_bytes + 15) / 16 * 16 + sizeof(unsigned int)) return DH_ERR_WORKSPACE;
-    lp.loss_out = loss_out;
-    const size_t smem = sizeof(float) * (size_t)o;
+    fin.n_layers = n_layers;
+    size_t o_counter;
+    if (ws_bytes < loss_ws_layout((size_t)chan, &o_counter)) return DH_ERR_WORKSPACE;
+    for (LossParams* q : {&pf, &pr}) {
+        q->G = grid; q->plan = plan; q->plan_cap = n_fg;
+        q->n_fg = n_fg; q->n_bg_orig = n_bg_orig; q->n_bg_trans = n_bg_trans; q->n_bg_common = n_bg_common;
+        q->fg_kind = fg_kind; q->bg_kind = bg_kind;
+        q->partial = static_cast<float*>(ws);
+    }
+    fin.done_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
+    fin.loss_out = loss_out;
     cudaStream_t st = as_stream(stream);
-    DH_CUDA_CHECK(cudaFuncSetAttribute(guidance_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     DH_CUDA_CHECK(cudaGetDevice(&dev));
     DH_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int grid_dim = sms;
-    if (grid_dim > chan) grid_dim = chan;
-    DH_CUDA_CHECK(cudaMemsetAsync(lp.done_counter, 0, sizeof(unsigned int), st));
-    guidance_loss_kernel<<<grid_dim, kLossThreads, smem, st>>>(p, lp);
-    DH_LAUNCH_CHECK();
+    // grids: persistent CTAs, as many as fit per SM
+    int grid_f = 0, grid_r = 0;
+    ResizeLayout lay;
+    memset(&lay, 0, sizeof(lay));
+    size_t smem_r = 0;
+    // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
+    auto flat_kernel = (plan_flags & 1) ? loss_flat_kernel<true> : loss_flat_kernel<false>;
+    if (pf.total_channels) {
+        int per_sm = 1;
+        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_kernel, kLossThreads, 0));
+        grid_f = sms * (per_sm < 1 ? 1 : per_sm);
+        if (grid_f > pf.total_channels) grid_f = pf.total_channels;
+    }
+    auto resize_kernel = grid == 64 ? loss_resize_kernel<64> : loss_resize_kernel<0>;
+    if (pr.total_channels) {
+        const int GG = grid * grid;
+        auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+        int cap = (box_cells > 0 && box_cells <= GG && bg_kind != 2) ? box_cells : GG;
+        if (!fg_kind && bg_kind != 2) cap = 4;
+        int o = 0;
+        lay.tab = o;    o += (int)(sizeof(LayerTabSmall) / 4);
+        lay.wo = o;     o += up4(hw_r);
+        lay.wt = o;     o += up4(hw_r);
+        lay.planes = o; o += up4(2 * hw_r);
+        lay.uc = o;     o += up4(cap);
+        lay.uo = o;     o += up4(cap);
+        lay.cnt = o;    o += up4(cap);
+        lay.tmp = o;    o += up4(h_r * grid);
+        lay.total = o;
+        lay.box_cap = cap;
+        smem_r = sizeof(float) * (size_t)o;
+        DH_CUDA_CHECK(cudaFuncSetAttribute(resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        int per_sm = 1;
+        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resize_kernel, kLossThreads, smem_r));
+        grid_r = sms * (per_sm < 1 ? 1 : per_sm);
+        if (grid_r > pr.total_channels) grid_r = pr.total_channels;
+    }
+    fin.total_ctas = (unsigned int)(grid_f + grid_r);
+    DH_CUDA_CHECK(cudaMemsetAsync(fin.done_counter, 0, sizeof(unsigned int), st));
+    if (grid_r) {
+        resize_kernel<<<grid_r, kLossThreads, smem_r, st>>>(pr, fin, lay);
+        DH_LAUNCH_CHECK();
+    }
+    if (grid_f) {
+        flat_kernel<<<grid_f, kLossThreads, 0, st>>>(pf, fin);
+        DH_LAUNCH_CHECK();
+    }
     return DH_OK;
 }
 

@@ -7,6 +7,7 @@ backward only rescales the stash by the incoming gradient - and exits on the dev
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -58,6 +59,23 @@ class LossPlan:
         N.check(lib.dh_build_loss_plan(p(fg_src), p(fg_dst), n_fg, p(bg_orig), self.n[1], p(bg_trans), self.n[2], p(bg_common),
                                        self.n[3], grid, N.ptr(self.buf), plan_bytes, N.ptr(ws), ws_bytes,
                                        N.stream_handle(torch.device(device))), "dh_build_loss_plan")
+        # one small read-back per edit: the plan header tells how big the box-local buffers of the kernel must be
+        hdr = self.buf[:64].cpu().numpy().tobytes()
+        n_pairs, box, flags = C.c_int(0), C.c_int(0), C.c_int(0)
+        N.check(lib.dh_loss_plan_info(hdr, C.byref(n_pairs), C.byref(box), C.byref(flags)), "dh_loss_plan_info")
+        self.n_pairs, self.box_cells, self.flags = n_pairs.value, box.value, flags.value
+        self._tables = {}
+
+    def resize_tables(self, h: int, w: int, fg_kind: int, bg_kind: int) -> torch.Tensor:
+        """Tables of a layer smaller than the loss grid (cached per shape and loss kind)."""
+        key = (h, w, fg_kind, bg_kind)
+        if key not in self._tables:
+            lib = N.load()
+            t = torch.empty(int(lib.dh_loss_resize_tables_bytes()), dtype=torch.uint8, device=self.buf.device)
+            N.check(lib.dh_build_loss_resize_tables(N.ptr(self.buf), self.n[0], self.grid, h, w, fg_kind, bg_kind, N.ptr(t),
+                                                    N.stream_handle(self.buf.device)), "dh_build_loss_resize_tables")
+            self._tables[key] = t
+        return self._tables[key]
 
 
 def _plan_for(pc, grid: int, device, keys=("fg_src", "fg_dst", "bg_orig", "bg_trans", "bg")) -> LossPlan:
@@ -98,12 +116,14 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         layers[i].grad = N.ptr(g) if g is not None else None
         layers[i].channels, layers[i].h, layers[i].w = c32.shape
         layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
+        h_, w_ = int(c32.shape[1]), int(c32.shape[2])
+        layers[i].resize_tables = None if (h_, w_) == (plan.grid, plan.grid) else N.ptr(plan.resize_tables(h_, w_, fg_kind, bg_kind))
     total_c = sum(int(c.shape[0]) for c in curs)
-    ws_bytes = 8 * total_c + 64
+    ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(int(c.shape[0]) for c in curs)))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
     n_fg, n_bo, n_bt, n_bc = plan.n
-    N.check(lib.dh_guidance_loss(layers, L, plan.grid, N.ptr(plan.buf), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind, N.ptr(out),
+    N.check(lib.dh_guidance_loss(layers, L, plan.grid, N.ptr(plan.buf), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags, fg_kind, bg_kind, N.ptr(out),
                                  N.ptr(ws), ws_bytes, N.stream_handle(dev)), "dh_guidance_loss")
     return out, grads
 

@@ -194,6 +194,7 @@ typedef struct dh_loss_layer {
     float* grad;            /* (C,h,w) out: weighted dL/dcur (may be NULL)    */
     int32_t channels, h, w;
     float fg_weight, bg_weight;
+    const void* resize_tables;   /* dh_build_loss_resize_tables output when (h,w) != (grid,grid), else NULL */
 } dh_loss_layer;
 
 /* Loss plan, built once per edit from the process_correspondences lists (int32 cell ids y*grid+x): the
@@ -206,10 +207,21 @@ int dh_build_loss_plan(const int32_t* fg_src, const int32_t* fg_dst, int n_fg,
                        const int32_t* bg_common, int n_bg_common, int grid,
                        void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
 
+/* Per-(plan, layer shape) tables of a layer smaller than the loss grid: bilinear taps, the transposed-resize weights,
+ * up^T(background multiplicities) and the active box.  Built once per edit and layer shape, reused every step. */
+size_t dh_loss_resize_tables_bytes(void);
+int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int w, int fg_kind, int bg_kind,
+                                void* tables, void* stream);
+
 size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels);
+/* Reads a HOST copy of the first 64 bytes of a plan: number of distinct pairs and the size (cells) of the box that
+ * contains every pair cell.  box_cells sizes the shared-memory buffers of the resized layers (0 = assume the whole grid);
+ * plan_flags bit 0 = every background multiplicity is 0 or 1 (selects the bit-mask instantiation; 0 is always safe). */
+int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags);
 /* n_* are the list lengths the plan was built from (they are the means' denominators). */
 int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan,
-                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind,
+                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int box_cells, int plan_flags,
+                     int fg_kind, int bg_kind,
                      float* loss_out /* device float[1 + 2*n_layers]: total, then fg_l, bg_l */,
                      void* ws, size_t ws_bytes, void* stream);
 /* grads *= *scale (device scalar); exits early on the device when *scale == 1. */
