@@ -12,6 +12,8 @@
 // conservative).
 #include "dh_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace dh {
 
 __device__ __forceinline__ int edit_points(const int32_t* n_points, int n_fixed, int e) {
@@ -120,12 +122,21 @@ __global__ void __launch_bounds__(256) splat_visible_kernel(const int32_t* __res
     visible[pi] = (fg && q >= 0 && winner[(size_t)e * P + q] == (uint32_t)i) ? 1 : 0;
 }
 
-// min / max of 1/depth over one image, one CTA per edit (deterministic, no atomics).  IEEE division is
-// monotone, so instead of dividing every pixel the kernel tracks min/max of the non-negative and of the
-// negative depths and takes the four reciprocals at the end: bit-identical to min/max over fl(1/d).
-__global__ void __launch_bounds__(1024) inv_minmax_kernel(const float* __restrict__ depth, int P, float* __restrict__ out) {
-    __shared__ float sm[4][32];
-    const int e = blockIdx.x;
+// min / max of 1/depth over one image.  A thread-block CLUSTER of 8 CTAs works on one edit: every CTA reduces an
+// eighth of the image into its own shared memory, then rank 0 reads the seven other partial results through
+// distributed shared memory (no scratch buffer, no atomics, deterministic).  IEEE division is monotone, so instead of
+// dividing every pixel the kernel tracks min/max of the non-negative and of the negative depths and takes four
+// reciprocals at the end: bit-identical to min/max over fl(1/d).
+constexpr int kMinMaxCluster = 8;
+
+__global__ void __cluster_dims__(kMinMaxCluster, 1, 1) __launch_bounds__(512)
+inv_minmax_kernel(const float* __restrict__ depth, int P, float* __restrict__ out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float sm[4][16];
+    __shared__ float part[4];
+    const int e = blockIdx.y;
+    const unsigned rank = cluster.block_rank();
     const float* d = depth + (size_t)e * P;
     const float inf = __int_as_float(0x7F800000);
     float pmin = inf, pmax = -inf, nmin = inf, nmax = -inf;     // over sign-bit-clear / sign-bit-set values
@@ -135,11 +146,11 @@ __global__ void __launch_bounds__(1024) inv_minmax_kernel(const float* __restric
         else { pmin = fminf(pmin, x); pmax = fmaxf(pmax, x); }
     };
     const int P4 = ((reinterpret_cast<uintptr_t>(d) & 15) == 0) ? P / 4 : 0;
-    for (int i = threadIdx.x; i < P4; i += blockDim.x) {
+    for (int i = rank * blockDim.x + threadIdx.x; i < P4; i += kMinMaxCluster * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(d) + i);
         take(v.x); take(v.y); take(v.z); take(v.w);
     }
-    for (int p = P4 * 4 + threadIdx.x; p < P; p += blockDim.x) take(d[p]);
+    for (int p = P4 * 4 + rank * blockDim.x + threadIdx.x; p < P; p += kMinMaxCluster * blockDim.x) take(d[p]);
     float r[4] = {pmin, -pmax, nmin, -nmax};                      // all four as minima
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -151,25 +162,34 @@ __global__ void __launch_bounds__(1024) inv_minmax_kernel(const float* __restric
     if (warp_id() == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            r[k] = lane_id() < (blockDim.x >> 5) ? sm[k][lane_id()] : inf;
+            r[k] = lane_id() < (int)(blockDim.x >> 5) ? sm[k][lane_id()] : inf;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) r[k] = fminf(r[k], __shfl_xor_sync(0xFFFFFFFFu, r[k], o));
-        }
-        if (lane_id() == 0) {
-            pmin = r[0]; pmax = -r[1]; nmin = r[2]; nmax = -r[3];
-            float mn = inf, mx = -inf;
-            if (pmin <= pmax) {           // some non-negative depth: reciprocals in [1/pmax, 1/pmin]
-                mn = fminf(mn, __fdiv_rn(1.0f, pmax));
-                mx = fmaxf(mx, __fdiv_rn(1.0f, pmin));
-            }
-            if (nmin <= nmax) {           // some negative depth: reciprocals in [1/nmax, 1/nmin]
-                mn = fminf(mn, __fdiv_rn(1.0f, nmax));
-                mx = fmaxf(mx, __fdiv_rn(1.0f, nmin));
-            }
-            out[e * 2] = mn;
-            out[e * 2 + 1] = mx;
+            if (lane_id() == 0) part[k] = r[k];
         }
     }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+        float q[4] = {inf, inf, inf, inf};
+        for (unsigned b = 0; b < kMinMaxCluster; ++b) {
+            const float* rp = cluster.map_shared_rank(part, b);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = fminf(q[k], rp[k]);
+        }
+        pmin = q[0]; pmax = -q[1]; nmin = q[2]; nmax = -q[3];
+        float mn = inf, mx = -inf;
+        if (pmin <= pmax) {           // some non-negative depth: reciprocals in [1/pmax, 1/pmin]
+            mn = fminf(mn, __fdiv_rn(1.0f, pmax));
+            mx = fmaxf(mx, __fdiv_rn(1.0f, pmin));
+        }
+        if (nmin <= nmax) {           // some negative depth: reciprocals in [1/nmax, 1/nmin]
+            mn = fminf(mn, __fdiv_rn(1.0f, nmax));
+            mx = fmaxf(mx, __fdiv_rn(1.0f, nmin));
+        }
+        out[e * 2] = mn;
+        out[e * 2 + 1] = mx;
+    }
+    cluster.sync();      // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 // normalize_depth(1/depth): (255 * (x - min)) / (max - min), fp32, same operation order as the reference.
@@ -217,7 +237,7 @@ int dh_splat_resolve(const uint64_t* zbuf, const uint32_t* winner, int B, int H,
     DH_LAUNCH_CHECK();
     if (inv_minmax) {
         DH_REQUIRE(depth_map);
-        inv_minmax_kernel<<<B, 1024, 0, st>>>(depth_map, H * W, inv_minmax);
+        inv_minmax_kernel<<<dim3(kMinMaxCluster, B), 512, 0, st>>>(depth_map, H * W, inv_minmax);
         DH_LAUNCH_CHECK();
     }
     return DH_OK;
@@ -236,7 +256,7 @@ int dh_splat_visible(const int32_t* pix, const uint32_t* winner, const int32_t* 
 
 int dh_inv_minmax(const float* depth, int B, int P, float* inv_minmax, void* stream) {
     DH_REQUIRE(depth && inv_minmax && B >= 1 && P >= 1);
-    inv_minmax_kernel<<<B, 1024, 0, as_stream(stream)>>>(depth, P, inv_minmax);
+    inv_minmax_kernel<<<dim3(kMinMaxCluster, B), 512, 0, as_stream(stream)>>>(depth, P, inv_minmax);
     DH_LAUNCH_CHECK();
     return DH_OK;
 }
