@@ -55,6 +55,9 @@ _SIGNATURES = {
     "dh_unproject_transform_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(dh_camera),
                                                C.POINTER(dh_rigid), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dh_transform_point_cloud_workspace_bytes": (c_size_t, [c_int]),
+    "dh_transform_point_cloud": (c_int, [c_void_p, c_void_p, c_int, C.POINTER(dh_rigid), c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_size_t, c_void_p]),
     "dh_project_points": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(dh_camera), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "dh_splat_zbuffer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -68,6 +71,7 @@ _SIGNATURES = {
     "dh_mask_clean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(C.c_uint32), c_int,
                               C.POINTER(C.c_uint32), c_int, c_void_p]),
     "dh_unpack_bits": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "dh_pack_mask_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dh_correspondences": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_process_correspondences": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -89,6 +93,8 @@ _SIGNATURES = {
     "dh_poisson_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dh_poisson_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.c_double,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dh_poisson_fill_source": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, C.c_double,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 # symbols include/dh_b200.h declares; tests check that every one of them is exported

@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(kTileThreads) fg_count_kernel(const float* __r
     }
 }
 
+// `points` != nullptr: the foreground points are taken from an (P,3) fp32 array instead of being unprojected
+// from `depth` (transform_point_cloud entry point).
 __global__ void __launch_bounds__(kTileThreads) fg_compact_kernel(
     const float* __restrict__ depth, const float* __restrict__ mask, int P, int W, int ntiles, CamDev cam,
     const float* __restrict__ xs, const float* __restrict__ ys, const int32_t* __restrict__ tile_counts,
     int32_t* __restrict__ fg_index, float* __restrict__ fgX, float* __restrict__ fgY, float* __restrict__ fgZ,
-    int32_t* __restrict__ n_fg) {
+    int32_t* __restrict__ n_fg, const float* __restrict__ points) {
     __shared__ int scan_smem[33];
     __shared__ int base_smem;
     const int e = blockIdx.y, tile = blockIdx.x;
@@ -155,7 +157,11 @@ __global__ void __launch_bounds__(kTileThreads) fg_compact_kernel(
         const int p = p0 + i;
         const int row = p / W, col = p - row * W;
         float X, Y, Z;
-        unproject(cam, depth[eo + p], xs[col], ys[row], X, Y, Z);
+        if (points) {
+            X = points[3 * (eo + p)]; Y = points[3 * (eo + p) + 1]; Z = points[3 * (eo + p) + 2];
+        } else {
+            unproject(cam, depth[eo + p], xs[col], ys[row], X, Y, Z);
+        }
         fg_index[eo + pos] = p;
         fgX[eo + pos] = X; fgY[eo + pos] = Y; fgZ[eo + pos] = Z;
         ++pos;
@@ -210,6 +216,38 @@ __global__ void __launch_bounds__(96) fg_centroid_kernel(const float* __restrict
     if (lane == 0) centroid[e * 3 + comp] = __fdiv_rn(s, (float)n);
 }
 
+// depth_transform.py:512-531 for one point: Rodrigues about the centroid + translation, fp32 -> fp64 in the
+// reference's operation order.
+__device__ __forceinline__ void rigid_point(float px, float py, float pz, float cx, float cy, float cz, const dh_rigid& rg,
+                                            double& X, double& Y, double& Z) {
+    const float qx = __fsub_rn(px, cx), qy = __fsub_rn(py, cy), qz = __fsub_rn(pz, cz);
+    const float ax = rg.axis[0], ay = rg.axis[1], az = rg.axis[2];
+    const float crx = __fsub_rn(__fmul_rn(ay, qz), __fmul_rn(az, qy));
+    const float cry = __fsub_rn(__fmul_rn(az, qx), __fmul_rn(ax, qz));
+    const float crz = __fsub_rn(__fmul_rn(ax, qy), __fmul_rn(ay, qx));
+    float d = __fmul_rn(qy, ay);
+    d = __fmaf_rn(qx, ax, d);
+    d = __fmaf_rn(qz, az, d);
+    const float t3x = __fmul_rn(ax, d), t3y = __fmul_rn(ay, d), t3z = __fmul_rn(az, d);
+    const double c = rg.cos_t, s = rg.sin_t, omc = __dsub_rn(1.0, c);
+    X = __dadd_rn(__dadd_rn(__dmul_rn((double)qx, c), __dmul_rn((double)crx, s)), __dmul_rn((double)t3x, omc));
+    Y = __dadd_rn(__dadd_rn(__dmul_rn((double)qy, c), __dmul_rn((double)cry, s)), __dmul_rn((double)t3y, omc));
+    Z = __dadd_rn(__dadd_rn(__dmul_rn((double)qz, c), __dmul_rn((double)crz, s)), __dmul_rn((double)t3z, omc));
+    X = __dadd_rn(__dadd_rn(X, (double)cx), rg.t[0]);
+    Y = __dadd_rn(__dadd_rn(Y, (double)cy), rg.t[1]);
+    Z = __dadd_rn(__dadd_rn(Z, (double)cz), rg.t[2]);
+}
+
+__global__ void __launch_bounds__(256) rigid_all_kernel(const float* __restrict__ points, int N, const dh_rigid* __restrict__ rigid,
+                                                        const float* __restrict__ centroid, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double X, Y, Z;
+    rigid_point(points[3 * (size_t)i], points[3 * (size_t)i + 1], points[3 * (size_t)i + 2], centroid[0], centroid[1], centroid[2],
+                rigid[0], X, Y, Z);
+    out[3 * (size_t)i] = X; out[3 * (size_t)i + 1] = Y; out[3 * (size_t)i + 2] = Z;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 main kernel: slot s < P -> background point s; slot s >= P -> foreground point j = s - P.
 // ------------------------------------------------------------------------------------------------
@@ -233,26 +271,7 @@ __global__ void __launch_bounds__(256) transform_project_kernel(
         const int j = slot - P;
         if (j >= n_fg[e]) return;
         const size_t eo = (size_t)e * P + j;
-        const dh_rigid rg = rigid[e];
-        const float cx = centroid[e * 3 + 0], cy = centroid[e * 3 + 1], cz = centroid[e * 3 + 2];
-        const float qx = __fsub_rn(fgX[eo], cx), qy = __fsub_rn(fgY[eo], cy), qz = __fsub_rn(fgZ[eo], cz);
-        const float ax = rg.axis[0], ay = rg.axis[1], az = rg.axis[2];
-        // np.cross(axis, q): separate fp32 multiplies and subtract
-        const float crx = __fsub_rn(__fmul_rn(ay, qz), __fmul_rn(az, qy));
-        const float cry = __fsub_rn(__fmul_rn(az, qx), __fmul_rn(ax, qz));
-        const float crz = __fsub_rn(__fmul_rn(ax, qy), __fmul_rn(ay, qx));
-        // np.dot(q, axis): sgemv accumulation fma(q2,a2, fma(q0,a0, q1*a1)); exact for single-component axes
-        float d = __fmul_rn(qy, ay);
-        d = __fmaf_rn(qx, ax, d);
-        d = __fmaf_rn(qz, az, d);
-        const float t3x = __fmul_rn(ax, d), t3y = __fmul_rn(ay, d), t3z = __fmul_rn(az, d);
-        const double c = rg.cos_t, s = rg.sin_t, omc = __dsub_rn(1.0, c);
-        X = __dadd_rn(__dadd_rn(__dmul_rn((double)qx, c), __dmul_rn((double)crx, s)), __dmul_rn((double)t3x, omc));
-        Y = __dadd_rn(__dadd_rn(__dmul_rn((double)qy, c), __dmul_rn((double)cry, s)), __dmul_rn((double)t3y, omc));
-        Z = __dadd_rn(__dadd_rn(__dmul_rn((double)qz, c), __dmul_rn((double)crz, s)), __dmul_rn((double)t3z, omc));
-        X = __dadd_rn(__dadd_rn(X, (double)cx), rg.t[0]);
-        Y = __dadd_rn(__dadd_rn(Y, (double)cy), rg.t[1]);
-        Z = __dadd_rn(__dadd_rn(Z, (double)cz), rg.t[2]);
+        rigid_point(fgX[eo], fgY[eo], fgZ[eo], centroid[e * 3 + 0], centroid[e * 3 + 1], centroid[e * 3 + 2], rigid[e], X, Y, Z);
     }
     int u, v;
     uint64_t key;
@@ -439,7 +458,8 @@ int dh_unproject_transform_project(const float* depth, const float* bg_depth, co
     dim3 tgrid(ntiles, B);
     fg_count_kernel<<<tgrid, kTileThreads, 0, st>>>(fg_mask, P, ntiles, tile_counts);
     DH_LAUNCH_CHECK();
-    fg_compact_kernel<<<tgrid, kTileThreads, 0, st>>>(depth, fg_mask, P, W, ntiles, cam, xs, ys, tile_counts, fg_index, fgX, fgY, fgZ, n_fg);
+    fg_compact_kernel<<<tgrid, kTileThreads, 0, st>>>(depth, fg_mask, P, W, ntiles, cam, xs, ys, tile_counts, fg_index, fgX, fgY, fgZ, n_fg,
+                                                      nullptr);
     DH_LAUNCH_CHECK();
     fg_centroid_kernel<<<B, 96, 0, st>>>(fgX, fgY, fgZ, n_fg, P, centroid);
     DH_LAUNCH_CHECK();
@@ -448,6 +468,43 @@ int dh_unproject_transform_project(const float* depth, const float* bg_depth, co
                                                    pix, zkey, points_out);
     DH_LAUNCH_CHECK();
     return DH_OK;
+}
+
+int dh_transform_point_cloud(const float* points, const float* mask, int N, const dh_rigid* rigid_host, double* out,
+                             float* centroid, int32_t* n_masked, void* ws, size_t ws_bytes, void* stream) {
+    DH_REQUIRE(points && mask && rigid_host && out && centroid && n_masked && ws && N >= 1);
+    // workspace = the K1 layout for one "image" of N pixels (+ the compacted index list)
+    size_t oc, orr, ox, oy, oz;
+    const size_t k1 = k1_ws_layout(1, N, &oc, &orr, &ox, &oy, &oz);
+    if (ws_bytes < k1 + sizeof(int32_t) * (size_t)N) return DH_ERR_WORKSPACE;
+    char* w = static_cast<char*>(ws);
+    int32_t* tile_counts = reinterpret_cast<int32_t*>(w + oc);
+    dh_rigid* rigid_dev = reinterpret_cast<dh_rigid*>(w + orr);
+    float* fgX = reinterpret_cast<float*>(w + ox);
+    float* fgY = reinterpret_cast<float*>(w + oy);
+    float* fgZ = reinterpret_cast<float*>(w + oz);
+    int32_t* index = reinterpret_cast<int32_t*>(w + k1);
+    cudaStream_t st = as_stream(stream);
+    const int ntiles = (N + kTile - 1) / kTile;
+    CamDev cam;
+    memset(&cam, 0, sizeof(cam));
+    DH_CUDA_CHECK(cudaMemcpyAsync(rigid_dev, rigid_host, sizeof(dh_rigid), cudaMemcpyHostToDevice, st));
+    fg_count_kernel<<<dim3(ntiles, 1), kTileThreads, 0, st>>>(mask, N, ntiles, tile_counts);
+    DH_LAUNCH_CHECK();
+    fg_compact_kernel<<<dim3(ntiles, 1), kTileThreads, 0, st>>>(nullptr, mask, N, N, ntiles, cam, nullptr, nullptr, tile_counts, index,
+                                                               fgX, fgY, fgZ, n_masked, points);
+    DH_LAUNCH_CHECK();
+    fg_centroid_kernel<<<1, 96, 0, st>>>(fgX, fgY, fgZ, n_masked, N, centroid);
+    DH_LAUNCH_CHECK();
+    rigid_all_kernel<<<(N + 255) / 256, 256, 0, st>>>(points, N, rigid_dev, centroid, out);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
+size_t dh_transform_point_cloud_workspace_bytes(int N) {
+    if (N < 1) return 0;
+    size_t a, b, c, d, e;
+    return k1_ws_layout(1, N, &a, &b, &c, &d, &e) + sizeof(int32_t) * (size_t)N;
 }
 
 int dh_project_points(const double* points, int N, int H, int W, const dh_camera* cam_host, int32_t* pix, uint64_t* zkey,

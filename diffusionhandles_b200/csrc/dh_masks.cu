@@ -52,6 +52,17 @@ __global__ void __launch_bounds__(256) morph_kernel(const uint32_t* __restrict__
     dst[(size_t)e * H * wpr + word] = acc;
 }
 
+// one warp per output word: bit b of word (row, w) = (mask[row][32 w + b] != 0)
+__global__ void __launch_bounds__(256) pack_bits_kernel(const float* __restrict__ mask, int H, int W, int wpr, uint32_t* __restrict__ bits) {
+    const int e = blockIdx.y;
+    const int word = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (word >= H * wpr) return;
+    const int row = word / wpr, col = (word - row * wpr) * 32 + lane_id();
+    const bool on = col < W && mask[(size_t)e * H * W + (size_t)row * W + col] != 0.0f;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, on);
+    if (lane_id() == 0) bits[(size_t)e * H * wpr + word] = b;
+}
+
 __global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t* __restrict__ bits, int n_words, uint8_t* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_words * 32) return;
@@ -298,6 +309,15 @@ int dh_mask_clean(const uint32_t* target_bits, uint32_t* cleaned_bits, uint32_t*
     rc = dh_morph_pass(cleaned_bits, tmp_bits, B, H, W, open_rows_host, open_k, open_k, 0, stream);
     if (rc) return rc;
     return dh_morph_pass(tmp_bits, cleaned_bits, B, H, W, open_rows_host, open_k, open_k, 1, stream);
+}
+
+int dh_pack_mask_bits(const float* mask, int B, int H, int W, uint32_t* bits, void* stream) {
+    DH_REQUIRE(mask && bits && B >= 1 && H >= 1 && W >= 1);
+    const int wpr = (W + 31) / 32;
+    dim3 grid((H * wpr + 7) / 8, B);
+    pack_bits_kernel<<<grid, 256, 0, as_stream(stream)>>>(mask, H, W, wpr, bits);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
 }
 
 int dh_unpack_bits(const uint32_t* bits, int n_words_total, uint8_t* out_u8, void* stream) {

@@ -44,7 +44,8 @@ __device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double
 }
 
 __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoissonThreads) poisson_cg_kernel(
-    const float* __restrict__ image, const uint32_t* __restrict__ mask_a, const uint32_t* __restrict__ mask_b, int H, int W,
+    const float* __restrict__ image, const uint32_t* __restrict__ mask_a, const uint32_t* __restrict__ mask_b,
+    const float* __restrict__ lap_source, int H, int W,
     int wpr, float* __restrict__ out, int max_iter, double rel_tol, int32_t* __restrict__ iters_out,
     uint32_t* __restrict__ ws_mask, int32_t* __restrict__ ws_list, int4* __restrict__ ws_nbr, double* __restrict__ ws_x,
     double* __restrict__ ws_r, double* __restrict__ ws_p, double* __restrict__ ws_ap) {
@@ -111,6 +112,17 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
         if (row < H - 1) { if (bit_at(mask, wpr, row + 1, col)) nb.y = q + W; else b += (double)img[q + W]; }
         if (col > 0) { if (bit_at(mask, wpr, row, col - 1)) nb.z = q - 1; else b += (double)img[q - 1]; }
         if (col < W - 1) { if (bit_at(mask, wpr, row, col + 1)) nb.w = q + 1; else b += (double)img[q + 1]; }
+        if (lap_source) {
+            // utils.py:49-94 (solve_laplacian_depth): b -= laplacian(source)[q], the 5-point stencil with zero padding,
+            // evaluated by scipy.ndimage.convolve in fp64 and stored as fp32
+            const float* sdat = lap_source + (size_t)e * P;
+            double lap = -4.0 * (double)sdat[q];
+            if (row > 0) lap += (double)sdat[q - W];
+            if (row < H - 1) lap += (double)sdat[q + W];
+            if (col > 0) lap += (double)sdat[q - 1];
+            if (col < W - 1) lap += (double)sdat[q + 1];
+            b -= (double)(float)lap;
+        }
         nbr[k] = nb;
         x[k] = 0.0; r[k] = b; p[q] = b;
         bb_part += b * b;
@@ -186,12 +198,19 @@ size_t dh_poisson_workspace_bytes(int B, int H, int W) {
 
 int dh_poisson_fill(const float* image, const uint32_t* mask_a_bits, const uint32_t* mask_b_bits, int B, int H, int W,
                     float* out, int max_iter, double rel_tol, int32_t* iters_out, void* ws, size_t ws_bytes, void* stream) {
+    return dh_poisson_fill_source(image, mask_a_bits, mask_b_bits, nullptr, B, H, W, out, max_iter, rel_tol, iters_out, ws, ws_bytes,
+                                  stream);
+}
+
+int dh_poisson_fill_source(const float* image, const uint32_t* mask_a_bits, const uint32_t* mask_b_bits, const float* lap_source,
+                           int B, int H, int W, float* out, int max_iter, double rel_tol, int32_t* iters_out, void* ws,
+                           size_t ws_bytes, void* stream) {
     DH_REQUIRE(image && mask_a_bits && out && ws && B >= 1 && H >= 1 && W >= 1 && image != out);
     size_t off[7];
     if (ws_bytes < poisson_layout(B, H, W, off)) return DH_ERR_WORKSPACE;
     char* w = static_cast<char*>(ws);
     poisson_cg_kernel<<<dim3(kPoissonCluster, B), kPoissonThreads, 0, as_stream(stream)>>>(
-        image, mask_a_bits, mask_b_bits, H, W, (W + 31) / 32, out, max_iter, rel_tol > 0 ? rel_tol : 1e-13, iters_out,
+        image, mask_a_bits, mask_b_bits, lap_source, H, W, (W + 31) / 32, out, max_iter, rel_tol > 0 ? rel_tol : 1e-13, iters_out,
         reinterpret_cast<uint32_t*>(w + off[0]), reinterpret_cast<int32_t*>(w + off[1]), reinterpret_cast<int4*>(w + off[2]),
         reinterpret_cast<double*>(w + off[3]), reinterpret_cast<double*>(w + off[4]), reinterpret_cast<double*>(w + off[5]),
         reinterpret_cast<double*>(w + off[6]));

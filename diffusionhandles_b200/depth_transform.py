@@ -120,25 +120,64 @@ def points_to_depth(points: torch.Tensor, intrinsics: torch.Tensor, output_size:
     return (depth_map[None, None], target.bool().cpu().numpy(), uv[0], uv[1], vis.cpu().numpy())
 
 
+def _pack_mask(mask_f32: torch.Tensor) -> torch.Tensor:
+    """(B,H,W) float mask (non-zero = set) -> row-padded bit planes (B,H,ceil(W/32)) int32."""
+    lib = N.load()
+    B, H, W = mask_f32.shape
+    bits = torch.empty((B, H, (W + 31) // 32), dtype=torch.int32, device=mask_f32.device)
+    N.check(lib.dh_pack_mask_bits(N.ptr(mask_f32, torch.float32, "mask"), B, H, W, N.ptr(bits), N.stream_handle(mask_f32.device)),
+            "dh_pack_mask_bits")
+    return bits
+
+
+def _poisson_device(image: torch.Tensor, mask_bits: torch.Tensor, lap_source: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = N.load()
+    B, H, W = image.shape
+    out = torch.empty_like(image)
+    ws_bytes = int(lib.dh_poisson_workspace_bytes(B, H, W))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=image.device)
+    N.check(lib.dh_poisson_fill_source(N.ptr(image, torch.float32, "image"), N.ptr(mask_bits), None,
+                                       N.ptr(lap_source, torch.float32, "lap_source") if lap_source is not None else None,
+                                       B, H, W, N.ptr(out), 0, 1e-13, None, N.ptr(ws), ws_bytes, N.stream_handle(image.device)),
+            "dh_poisson_fill_source")
+    return out
+
+
 def poisson_solve(input_image, mask):
     """depth_transform.py:535-587 - masked Poisson fill (fp64 CG on the device; SuperLU in the reference).
     NumPy in / NumPy out like the reference; the image is processed on the current CUDA device."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    arr = np.asarray(input_image)
+    img = torch.as_tensor(arr, dtype=torch.float32, device=dev)[None].contiguous()
+    m = torch.as_tensor(np.asarray(mask) != 0, device=dev).to(torch.float32)[None].contiguous()
+    out = _poisson_device(img, _pack_mask(m))
+    return out[0].cpu().numpy().astype(arr.dtype)
+
+
+def transform_point_cloud(points, axis, angle_degrees, x, y, z, mask):
+    """depth_transform.py:461-533 - rotate a point image about the centroid of the masked points and translate it.
+    points (S,S,3) fp32 (NumPy or torch), mask (S,S); returns ``(rotated_points (S,S,3) float64 ndarray,
+    modified_indices (S*S,) bool ndarray)`` like the reference (which hard-codes S = 512; any S works here)."""
     lib = N.load()
     dev = torch.device("cuda", torch.cuda.current_device())
-    img = torch.as_tensor(np.asarray(input_image), dtype=torch.float32, device=dev).contiguous()
-    H, W = img.shape
-    wpr = (W + 31) // 32
-    m = torch.zeros((H, wpr * 32), dtype=torch.bool, device=dev)
-    m[:, :W] = torch.as_tensor(np.asarray(mask) != 0, device=dev)
-    weights = (2 ** torch.arange(32, dtype=torch.int64, device=dev))
-    bits = (m.view(H, wpr, 32).to(torch.int64) * weights).sum(-1)
-    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).contiguous()
-    out = torch.empty_like(img)
-    ws_bytes = int(lib.dh_poisson_workspace_bytes(1, H, W))
+    pts = torch.as_tensor(np.asarray(points) if not isinstance(points, torch.Tensor) else points).to(device=dev, dtype=torch.float32)
+    shape = tuple(pts.shape)
+    pts = pts.reshape(-1, 3).contiguous()
+    n = pts.shape[0]
+    mk = torch.as_tensor(np.asarray(mask) if not isinstance(mask, torch.Tensor) else mask).to(device=dev)
+    mk_flat = (mk.reshape(-1) != 0)
+    if mk_flat.numel() != n:
+        raise ValueError("mask must have one entry per point")
+    rg = make_rigid(angle_degrees, axis, [x, y, z])
+    rg.t[:] = [float(x), float(y), float(z)]          # the reference adds the Python floats as given
+    out = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    cen = torch.empty(3, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.dh_transform_point_cloud_workspace_bytes(n))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    N.check(lib.dh_poisson_fill(N.ptr(img), N.ptr(bits), None, 1, H, W, N.ptr(out), 0, 1e-13, None, N.ptr(ws), ws_bytes,
-                                N.stream_handle(dev)), "dh_poisson_fill")
-    return out.cpu().numpy().astype(np.asarray(input_image).dtype)
+    N.check(lib.dh_transform_point_cloud(N.ptr(pts), N.ptr(mk_flat.to(torch.float32).contiguous()), n, C.byref(rg), N.ptr(out), N.ptr(cen),
+                                         N.ptr(cnt), N.ptr(ws), ws_bytes, N.stream_handle(dev)), "dh_transform_point_cloud")
+    return out.reshape(shape).cpu().numpy(), mk_flat.cpu().numpy()
 
 
 def _empty_mask_result(depth, use_input_depth_normalization):

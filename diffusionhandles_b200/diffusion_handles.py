@@ -57,7 +57,22 @@ class DiffusionHandles:
         return null_text_emb, init_noise, activations, latent_image
 
     def set_foreground(self, depth: torch.Tensor, fg_mask: torch.Tensor, bg_depth: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("set_foreground (solve_laplacian_depth pre-processing) is a 'next' row, SURVEY.md 8(f) rank 1")
+        """diffusion_handles.py:88-110: background depth = input depth with the (15 px dilated) foreground hole filled by
+        a Poisson problem driven by the Laplacian of ``bg_depth``.  Entirely on the device: the dilation is one pass of the
+        bit-packed morphology kernel with the 31 x 31 diamond that 15 iterations of SciPy's cross element amount to."""
+        from . import _native as N
+        from .depth_transform import _pack_mask, _poisson_device
+        lib = N.load()
+        dev = depth.device
+        H, W = depth.shape[-2:]
+        d = depth.reshape(1, H, W).to(torch.float32).contiguous()
+        b = bg_depth.reshape(1, H, W).to(device=dev, dtype=torch.float32).contiguous()
+        bits = _pack_mask((fg_mask.reshape(1, H, W).to(dev) != 0).to(torch.float32).contiguous())
+        r = 15
+        rows = N.u32_array([((1 << (2 * (r - abs(i - r)) + 1)) - 1) << abs(i - r) for i in range(2 * r + 1)])
+        dil = torch.empty_like(bits)
+        N.check(lib.dh_morph_pass(N.ptr(bits), N.ptr(dil), 1, H, W, rows, 2 * r + 1, 2 * r + 1, 1, N.stream_handle(dev)), "dh_morph_pass")
+        return _poisson_device(d, dil, lap_source=b)[None]
 
     def transform_foreground(self, depth: torch.Tensor, prompt: str, fg_mask: torch.Tensor, bg_depth: torch.Tensor,
                              null_text_emb: torch.Tensor, init_noise: torch.Tensor, activations: list,

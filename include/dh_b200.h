@@ -109,6 +109,13 @@ int dh_unproject_transform_project(const float* depth, const float* bg_depth, co
                                    float* centroid, double* points_out,
                                    void* ws, size_t ws_bytes, void* stream);
 
+/* ---- row 3: transform_point_cloud, depth_transform.py:461-533 -----------------------------------------
+ * points (N,3) fp32, mask (N) fp32 (non-zero = selected): Rodrigues rotation about the fp32 sequential centroid of
+ * the selected points + translation, applied to ALL N points -> out (N,3) fp64; centroid float[3]; n_masked int32. */
+size_t dh_transform_point_cloud_workspace_bytes(int N);
+int dh_transform_point_cloud(const float* points, const float* mask, int N, const dh_rigid* rigid_host, double* out,
+                             float* centroid, int32_t* n_masked, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- row 5 (projection only): points (N,3) fp64 -> pix, zkey;  depth_transform.py:666-687 --------- */
 int dh_project_points(const double* points, int N, int H, int W, const dh_camera* cam_host,
                       int32_t* pix, uint64_t* zkey, int32_t* u, int32_t* v, void* stream);
@@ -152,6 +159,8 @@ int dh_morph_pass(const uint32_t* src_bits, uint32_t* dst_bits, int B, int H, in
 int dh_mask_clean(const uint32_t* target_bits, uint32_t* cleaned_bits, uint32_t* tmp_bits, int B, int H, int W,
                   const uint32_t* close_rows_host, int close_k, const uint32_t* open_rows_host, int open_k, void* stream);
 int dh_unpack_bits(const uint32_t* bits, int n_words_total, uint8_t* out_u8, void* stream);
+/* float mask (B,H,W), non-zero = set -> row-padded bit planes uint32[B][H][ceil(W/32)] */
+int dh_pack_mask_bits(const float* mask, int B, int H, int W, uint32_t* bits, void* stream);
 
 /* ---- row 6: correspondences, depth_transform.py:299-343 -------------------------------------------
  * For fg point j (raster order of the source): keep iff visible and cleaned[pix]; emits int64 (n,4)
@@ -234,6 +243,11 @@ int dh_scale_inplace(float* data, size_t n, const float* scale, void* stream);
 size_t dh_poisson_workspace_bytes(int B, int H, int W);
 int dh_poisson_fill(const float* image, const uint32_t* mask_a_bits, const uint32_t* mask_b_bits, int B, int H, int W,
                     float* out, int max_iter, double rel_tol, int32_t* iters_out, void* ws, size_t ws_bytes, void* stream);
+/* Same system with a source term: right-hand side -= laplacian(lap_source) (5-point stencil, zero padding, rounded to
+ * fp32) - solve_laplacian_depth, utils.py:49-102, used by DiffusionHandles.set_foreground (diffusion_handles.py:105-108). */
+int dh_poisson_fill_source(const float* image, const uint32_t* mask_a_bits, const uint32_t* mask_b_bits,
+                           const float* lap_source, int B, int H, int W, float* out, int max_iter, double rel_tol,
+                           int32_t* iters_out, void* ws, size_t ws_bytes, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -126,17 +126,18 @@ def normalize_axis(axis: Sequence[float]) -> np.ndarray:
 
 
 def rigid_transform_fg(p: np.ndarray, axis: Sequence[float], angle_degrees: float,
-                       t: Sequence[float]) -> Tuple[np.ndarray, np.ndarray]:
+                       t: Sequence[float], centroid: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     """Rodrigues rotation about the centroid + translation for the N_fg masked points (raster order).
 
     p (N_fg,3) fp32 -> (N_fg,3) fp64, centroid (3,) fp32.  depth_transform.py:492-531, SURVEY.md A.2/A.9.
+    With ``centroid`` given, the points are rotated about it instead of about their own centroid.
     """
     p = np.asarray(p, dtype=f32)
     n = p.shape[0]
     a = normalize_axis(axis)
     angle = np.radians(angle_degrees)
     c, s = np.cos(angle), np.sin(angle)                     # fp64 scalars
-    cen = (sequential_sum_f32(p) / f32(n)).astype(f32)
+    cen = (sequential_sum_f32(p) / f32(n)).astype(f32) if centroid is None else np.asarray(centroid, f32)
     q = (p - cen).astype(f32)
     cr = np.stack([
         ((a[1] * q[:, 2]).astype(f32) - (a[2] * q[:, 1]).astype(f32)).astype(f32),
@@ -150,6 +151,17 @@ def rigid_transform_fg(p: np.ndarray, axis: Sequence[float], angle_degrees: floa
     r = (q.astype(f64) * c + cr.astype(f64) * s) + t3.astype(f64) * (1 - c)
     r = (r + cen.astype(f64)) + np.array([t[0], t[1], t[2]], dtype=f64)
     return r, cen
+
+
+def transform_point_cloud(points: np.ndarray, axis, angle_degrees: float, x: float, y: float, z: float, mask: np.ndarray):
+    """depth_transform.py:461-533 with the hard-coded 512 generalised: rotates ALL points about the fp32 sequential
+    centroid of the masked ones.  Returns ((S,S,3) fp64, (S*S,) bool)."""
+    points = np.asarray(points, dtype=f32)
+    m = np.asarray(mask).astype(bool)
+    flat = points.reshape(-1, 3)
+    cen = (sequential_sum_f32(flat[m.reshape(-1)]) / f32(int(m.sum()))).astype(f32)
+    r, _ = rigid_transform_fg(flat, axis, angle_degrees, (x, y, z), centroid=cen)
+    return r.reshape(points.shape), m.reshape(-1)
 
 
 # --------------------------------------------------------------------------------------------
@@ -344,6 +356,39 @@ def poisson_solve(image: np.ndarray, mask: np.ndarray) -> np.ndarray:
     A = scipy.sparse.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
     sol = scipy.sparse.linalg.spsolve(A, b)
     out[ys, xs] = sol
+    return out
+
+
+def solve_laplacian_depth(fg_depth: np.ndarray, bg_depth: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """utils.py:49-102: Poisson fill of ``fg_depth`` inside ``mask`` whose source term is the Laplacian of ``bg_depth``
+    (scipy.ndimage.convolve with the 5-point kernel, zero padding, result in the input dtype)."""
+    import scipy.ndimage
+    import scipy.sparse
+    import scipy.sparse.linalg
+    fg = np.asarray(fg_depth)
+    mask = np.asarray(mask).astype(bool)
+    ys, xs = np.where(mask)
+    n = len(ys)
+    out = fg.copy()
+    if n == 0:
+        return out
+    H, W = fg.shape
+    lap = scipy.ndimage.convolve(np.asarray(bg_depth), np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]]), mode="constant")
+    index = -np.ones((H, W), dtype=np.int64)
+    index[ys, xs] = np.arange(n)
+    rows, cols, vals = [np.arange(n)], [np.arange(n)], [np.full(n, 4.0)]
+    b = np.zeros(n)
+    for dy, dx in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+        ny, nx = ys + dy, xs + dx
+        inside = (ny >= 0) & (ny < H) & (nx >= 0) & (nx < W)
+        nyc, nxc = np.clip(ny, 0, H - 1), np.clip(nx, 0, W - 1)
+        unk = inside & mask[nyc, nxc]
+        known = inside & ~mask[nyc, nxc]
+        rows.append(np.nonzero(unk)[0]); cols.append(index[nyc[unk], nxc[unk]]); vals.append(np.full(unk.sum(), -1.0))
+        b[known] += fg[nyc[known], nxc[known]]
+    b -= lap[ys, xs]
+    A = scipy.sparse.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    out[ys, xs] = scipy.sparse.linalg.spsolve(A, b)
     return out
 
 

@@ -163,6 +163,22 @@ def make_small_goldens(ref):
             lb = ref.losses.compute_background_loss(cur, orig, pc, 1, (64, 64), loss_type=lt)
             out[f"loss_{tag}/bg_{lt}"] = lb.detach().numpy()
             out[f"loss_{tag}/bg_{lt}_grad"] = torch.autograd.grad(lb, cur)[0].numpy()
+    # transform_point_cloud (hard-wired to 512 x 512 in the reference, depth_transform.py:531)
+    depth, bg, mask = O.synthetic_scene(S=512, seed=9, radius=70.0)
+    pts = dt.depth_to_world_coords(torch.from_numpy(depth)[None, None], K).numpy()
+    rot, mod = dt.transform_point_cloud(pts, np.array([0.0, 1.0, 0.0], np.float32), 33.0, 0.25, -0.5, 0.125, mask)
+    out["tpc/sha"] = np.frombuffer(bytes.fromhex(sha(rot)), dtype=np.uint8)
+    out["tpc/rows"] = rot[::64].copy()
+    out["tpc/mod_count"] = np.int64(mod.sum())
+    # solve_laplacian_depth + the set_foreground recipe (diffusion_handles.py:105-108), resolution generic
+    import scipy.ndimage
+    for tag, (S, it) in {"s96": (96, 4), "s160": (160, 15)}.items():
+        depth, bg, mask = O.synthetic_scene(S=S, seed=12, radius=S / 6)
+        dil = scipy.ndimage.binary_dilation(mask.astype(bool), iterations=it)
+        sol = ref.utils.solve_laplacian_depth(depth, bg, dil)
+        out[f"sld_{tag}/S_it"] = np.array([S, it])
+        out[f"sld_{tag}/dilated"] = np.packbits(dil)
+        out[f"sld_{tag}/solution"] = sol
     np.savez_compressed(os.path.join(GOLDEN_DIR, "small_cases.npz"), **out)
     print(f"[golden] small cases: {len(out)} arrays")
 

@@ -476,3 +476,44 @@ def test_diffusion_handles_facade_transform_foreground(dev, K, golden_pc):
     assert disp.shape == (1, 1, 512, 512)
     with pytest.raises(NotImplementedError):
         DiffusionHandles().generate_input_image(td, "x")
+
+
+def test_transform_point_cloud_golden(dev, K, golden_small):
+    """depth_transform.py:461-533: fp64 output bit-exact against the reference (single-component axis)."""
+    from diffusionhandles_b200 import depth_transform as dt
+    g = golden_small
+    depth, bg, mask = O.synthetic_scene(S=512, seed=9, radius=70.0)
+    pts = dt.depth_to_world_coords(torch.from_numpy(depth).to(dev)[None, None], K).cpu().numpy()
+    rot, mod = dt.transform_point_cloud(pts, np.array([0.0, 1.0, 0.0], np.float32), 33.0, 0.25, -0.5, 0.125, mask)
+    assert rot.dtype == np.float64 and rot.shape == (512, 512, 3) and mod.dtype == bool
+    assert bytes.fromhex(sha(rot)) == g["tpc/sha"].tobytes()
+    assert int(mod.sum()) == int(g["tpc/mod_count"])
+    # another resolution against the oracle
+    depth, bg, mask = O.synthetic_scene(S=200, seed=10)
+    pts = O.depth_to_world_coords(depth, K_NP)
+    rot, _ = dt.transform_point_cloud(pts, [1.0, 0.0, 0.0], -20.0, 0.1, 0.2, 0.3, mask)
+    ref, _ = O.transform_point_cloud(pts, [1.0, 0.0, 0.0], -20.0, 0.1, 0.2, 0.3, mask)
+    assert np.array_equal(rot, ref)
+
+
+@pytest.mark.parametrize("tag", ["s96", "s160"])
+def test_solve_laplacian_depth_and_set_foreground(dev, golden_small, tag):
+    """utils.py:49-102 / diffusion_handles.py:88-110 against the reference's SuperLU solution (tolerance: CG in fp64)."""
+    import scipy.ndimage
+    from diffusionhandles_b200 import DiffusionHandles
+    from diffusionhandles_b200.utils import solve_laplacian_depth
+    g = golden_small
+    S, it = (int(v) for v in g[f"sld_{tag}/S_it"])
+    depth, bg, mask = O.synthetic_scene(S=S, seed=12, radius=S / 6)
+    dil = np.unpackbits(g[f"sld_{tag}/dilated"])[: S * S].reshape(S, S).astype(bool)
+    ref = g[f"sld_{tag}/solution"]
+    sol = solve_laplacian_depth(depth, bg, dil)
+    assert sol.dtype == np.float32 and sol.shape == (S, S)
+    assert np.array_equal(sol[~dil], ref[~dil])
+    assert np.abs(sol - ref).max() <= 1e-4 * np.abs(ref).max()
+    if it == 15:    # the full set_foreground recipe (dilation by 15 iterations of the cross element on the device)
+        td, tb, tm = (torch.from_numpy(a).to(dev)[None, None] for a in (depth, bg, mask))
+        out = DiffusionHandles().to(dev).set_foreground(td, tm, tb)
+        assert out.shape == (1, 1, S, S) and out.device.type == "cuda"
+        assert np.abs(out[0, 0].cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+        assert np.array_equal(scipy.ndimage.binary_dilation(mask.astype(bool), iterations=15), dil)

@@ -163,3 +163,25 @@ def test_dense_map_and_gather_properties(golden_pc):
         D = O.warp_gather_dense(A, m).reshape(3, -1)
         assert np.array_equal(D[:, m < 0], np.zeros((3, int((m < 0).sum())), np.float32))
         assert np.array_equal(D[:, m >= 0], A.reshape(3, -1)[:, m[m >= 0]])
+
+
+def test_transform_point_cloud_golden(golden_small):
+    g = golden_small
+    depth, bg, mask = O.synthetic_scene(S=512, seed=9, radius=70.0)
+    pts = O.depth_to_world_coords(depth, K)
+    rot, mod = O.transform_point_cloud(pts, np.array([0.0, 1.0, 0.0], np.float32), 33.0, 0.25, -0.5, 0.125, mask)
+    assert rot.dtype == np.float64 and rot.shape == (512, 512, 3)
+    assert bytes.fromhex(sha(rot)) == g["tpc/sha"].tobytes()
+    assert np.array_equal(rot[::64], g["tpc/rows"]) and int(mod.sum()) == int(g["tpc/mod_count"])
+
+
+@pytest.mark.parametrize("tag", ["s96", "s160"])
+def test_solve_laplacian_depth_golden(golden_small, tag):
+    import scipy.ndimage
+    g = golden_small
+    S, it = (int(v) for v in g[f"sld_{tag}/S_it"])
+    depth, bg, mask = O.synthetic_scene(S=S, seed=12, radius=S / 6)
+    dil = scipy.ndimage.binary_dilation(mask.astype(bool), iterations=it)
+    assert np.array_equal(np.packbits(dil), g[f"sld_{tag}/dilated"])
+    sol = O.solve_laplacian_depth(depth, bg, dil)
+    assert sol.dtype == np.float32 and np.array_equal(sol, g[f"sld_{tag}/solution"])
