@@ -76,7 +76,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -262,7 +262,6 @@ def run_ours(args):
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -272,6 +271,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----
     per_launch = time_kernel_steps(step, max(args.steps, 10), 3, dev)
+    clocks = sampler.stop()          # sampled over the K timed steps and the per-launch roofline loop
     k3_ms = float(np.mean(per_launch))
     achieved = ALGO_BYTES_PER_WARP * n_edits / (k3_ms * 1e-3) / 1e9
     peak, peak_kind = measured_peak_hbm()
@@ -333,6 +333,7 @@ def run_ours(args):
     if world > 1:
         from diffusionhandles_b200.batch import gather_records
         rec = torch.stack([wl["n_corr"].to(torch.int64), outs[0].flatten(1).sum(1).double().view(torch.int64)], dim=1).contiguous()
+        gather_records(rec, dst=0)      # first call sets up the NCCL communicator
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         gathered = gather_records(rec, dst=0)

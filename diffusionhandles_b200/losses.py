@@ -65,6 +65,7 @@ class LossPlan:
         N.check(lib.dh_loss_plan_info(hdr, C.byref(n_pairs), C.byref(box), C.byref(flags)), "dh_loss_plan_info")
         self.n_pairs, self.box_cells, self.flags = n_pairs.value, box.value, flags.value
         self._tables = {}
+        self._runners = {}
 
     def resize_tables(self, h: int, w: int, fg_kind: int, bg_kind: int) -> torch.Tensor:
         """Tables of a layer smaller than the loss grid (cached per shape and loss kind)."""
@@ -93,6 +94,13 @@ def _plan_for(pc, grid: int, device, keys=("fg_src", "fg_dst", "bg_orig", "bg_tr
     return plan
 
 
+def _as_f32(t: torch.Tensor, dev) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype is torch.float32 and t.device == dev and t.is_contiguous():
+        return t
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
 def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_grad: Sequence[bool],
             fgw: Sequence[float], bgw: Sequence[float], plan: LossPlan, fg_kind: int,
             bg_kind: int) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
@@ -101,30 +109,42 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
     if dev.type != "cuda":
         raise N.NativeLibraryError("guidance losses run on CUDA only; there is no CPU fallback")
     L = len(curs)
-    layers = (N.dh_loss_layer * L)()
+    shapes = tuple(tuple(c.shape) for c in curs)
+    key = (shapes, fg_kind, bg_kind)
+    runner = plan._runners.get(key)
+    if runner is None:
+        # per (plan, shapes): the ctypes layer array, the workspace and the resize tables are created once
+        for c, o in zip(curs, origs):
+            if c.dim() != 3 or tuple(c.shape) != tuple(o.shape):
+                raise ValueError("activations must be (C,h,w) with matching recorded activations")
+        layers = (N.dh_loss_layer * L)()
+        tabs = []
+        for i, sh in enumerate(shapes):
+            layers[i].channels, layers[i].h, layers[i].w = sh
+            t = None if (sh[1], sh[2]) == (plan.grid, plan.grid) else plan.resize_tables(sh[1], sh[2], fg_kind, bg_kind)
+            tabs.append(t)
+            layers[i].resize_tables = N.ptr(t) if t is not None else None
+        ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(sh[0] for sh in shapes)))
+        runner = (layers, torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes, tabs)
+        plan._runners[key] = runner
+    layers, ws, ws_bytes, _ = runner
     grads: List[Optional[torch.Tensor]] = []
     keep = []
-    for i, (c, o) in enumerate(zip(curs, origs)):
-        if c.dim() != 3 or tuple(c.shape) != tuple(o.shape):
+    for i in range(L):
+        if tuple(origs[i].shape) != shapes[i]:
             raise ValueError("activations must be (C,h,w) with matching recorded activations")
-        c32 = c.detach().to(torch.float32).contiguous()
-        o32 = o.detach().to(device=dev, dtype=torch.float32).contiguous()
+        c32, o32 = _as_f32(curs[i], dev), _as_f32(origs[i], dev)
         g = torch.empty_like(c32) if want_grad[i] else None
-        keep += [c32, o32]
+        keep.append((c32, o32))
         grads.append(g)
-        layers[i].cur, layers[i].orig = N.ptr(c32), N.ptr(o32)
-        layers[i].grad = N.ptr(g) if g is not None else None
-        layers[i].channels, layers[i].h, layers[i].w = c32.shape
+        layers[i].cur, layers[i].orig = c32.data_ptr(), o32.data_ptr()
+        layers[i].grad = g.data_ptr() if g is not None else None
         layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
-        h_, w_ = int(c32.shape[1]), int(c32.shape[2])
-        layers[i].resize_tables = None if (h_, w_) == (plan.grid, plan.grid) else N.ptr(plan.resize_tables(h_, w_, fg_kind, bg_kind))
-    total_c = sum(int(c.shape[0]) for c in curs)
-    ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(int(c.shape[0]) for c in curs)))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
     n_fg, n_bo, n_bt, n_bc = plan.n
-    N.check(lib.dh_guidance_loss(layers, L, plan.grid, N.ptr(plan.buf), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags, fg_kind, bg_kind, N.ptr(out),
-                                 N.ptr(ws), ws_bytes, N.stream_handle(dev)), "dh_guidance_loss")
+    N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
+                                 fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 torch.cuda.current_stream(dev).cuda_stream), "dh_guidance_loss")
     return out, grads
 
 
@@ -145,11 +165,14 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, g_total, _g_parts):
         lib = N.load()
         res = [None] * (1 + ctx.n_inputs)
+        scale, st = None, None
         for i, g in enumerate(ctx.grads):
             if g is None:
                 continue
-            scale = g_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
-            N.check(lib.dh_scale_inplace(N.ptr(g), g.numel(), N.ptr(scale), N.stream_handle(g.device)), "dh_scale_inplace")
+            if scale is None:
+                scale = _as_f32(g_total, g.device).reshape(1)
+                st = torch.cuda.current_stream(g.device).cuda_stream
+            N.check(lib.dh_scale_inplace(g.data_ptr(), g.numel(), scale.data_ptr(), st), "dh_scale_inplace")
             res[1 + i] = g
         ctx.grads = None
         return tuple(res)
