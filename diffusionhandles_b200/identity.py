@@ -1,0 +1,57 @@
+"""Input-image identity: the recorded activation stacks and the inversion results that the
+reference's drivers cache as ``input_image_identity.npz`` (test/test_diffusion_handles.py:85-114,
+webapp/webapps/diffhandles_webapp.py:82-96): keys ``null_text_emb``, ``init_noise``, ``activations1..3``,
+``latent_image``.  The stacks are ~1 GB fp32 per image; they are loaded once through a pinned staging buffer and stay
+resident on the device, so every guidance step reads them from HBM.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+import torch
+
+KEYS = ("null_text_emb", "init_noise", "activations1", "activations2", "activations3", "latent_image")
+
+
+@dataclass
+class InputImageIdentity:
+    null_text_emb: torch.Tensor
+    init_noise: torch.Tensor
+    activations: List[torch.Tensor]      # three (T, C, h, w) fp32 stacks, device resident
+    latent_image: torch.Tensor
+
+    def recorded(self, t_idx: int) -> List[torch.Tensor]:
+        """The three recorded (C,h,w) activation maps of denoising step ``t_idx`` (contiguous views, no copy)."""
+        return [a[t_idx] for a in self.activations]
+
+    def nbytes(self) -> int:
+        return sum(a.numel() * a.element_size() for a in self.activations)
+
+
+def save_identity(path: str, identity: InputImageIdentity) -> None:
+    """Writes the reference's ``.npz`` layout (np.savez, uncompressed)."""
+    arrays = {"null_text_emb": identity.null_text_emb, "init_noise": identity.init_noise, "latent_image": identity.latent_image}
+    arrays.update({f"activations{i + 1}": a for i, a in enumerate(identity.activations)})
+    np.savez(path, **{k: v.detach().cpu().numpy() for k, v in arrays.items()})
+
+
+def load_identity(path: str, device: torch.device) -> InputImageIdentity:
+    """Reads the reference's ``.npz`` layout and places everything on ``device`` (pinned staging, async copies)."""
+    device = torch.device(device)
+    out = {}
+    with np.load(path) as z:
+        missing = [k for k in KEYS if k not in z.files]
+        if missing:
+            raise KeyError(f"{path} is not an input-image identity file (missing {missing})")
+        for k in KEYS:
+            host = torch.from_numpy(np.ascontiguousarray(z[k]))
+            if device.type == "cuda":
+                host = host.pin_memory()
+            out[k] = host.to(device, non_blocking=True)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    return InputImageIdentity(null_text_emb=out["null_text_emb"], init_noise=out["init_noise"],
+                              activations=[out["activations1"], out["activations2"], out["activations3"]],
+                              latent_image=out["latent_image"])

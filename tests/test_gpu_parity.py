@@ -517,3 +517,79 @@ def test_solve_laplacian_depth_and_set_foreground(dev, golden_small, tag):
         assert out.shape == (1, 1, S, S) and out.device.type == "cuda"
         assert np.abs(out[0, 0].cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
         assert np.array_equal(scipy.ndimage.binary_dilation(mask.astype(bool), iterations=15), dil)
+
+
+def test_guided_loop_with_toy_unet(dev, golden_pc):
+    """8(f) rank 4: the guided denoising loop (guided_stable_diffuser.py:377-480) around an injected toy U-Net.  The
+    latents after a few guided steps must match the same loop written with stock PyTorch ops for the reference's
+    loss formulas (losses.py) and autograd - i.e. the fused K4 launch is a drop-in inside a real backward pass."""
+    from diffusionhandles_b200.guided_loop import guided_denoise
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser, make_guidance_weight_schedule
+    _, gp = golden_pc
+    corr = gp["cfg1/corr"].astype(np.int64)
+    pc = GuidedStableDiffuser().process_correspondences(torch.from_numpy(corr), 512, 0)
+    torch.manual_seed(0)
+    chans = [24, 16, 8]
+
+    class ToyUNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c0 = torch.nn.Conv2d(4, chans[0], 3, stride=2, padding=1)      # 32 x 32
+            self.c1 = torch.nn.Conv2d(4, chans[1], 3, padding=1)                # 64 x 64
+            self.c2 = torch.nn.Conv2d(4, chans[2], 3, padding=1)
+            self.out = torch.nn.Conv2d(chans[2], 4, 3, padding=1)
+
+        def forward(self, x, t):
+            a = [torch.tanh(self.c0(x)), torch.tanh(self.c1(x)), torch.tanh(self.c2(x))]
+            return self.out(a[2]) * 0.1, a
+
+    net = ToyUNet().to(dev)
+    T = 3
+    lat0 = torch.randn(1, 4, 64, 64, device=dev)
+    with torch.no_grad():
+        orig = [torch.stack([net(torch.randn(1, 4, 64, 64, device=dev), 0)[1][l][0] for _ in range(T)]) for l in range(3)]
+
+    def sched_step(noise, t, lat):
+        return lat - 0.05 * noise
+
+    ours = guided_denoise(lat0, list(range(T)), net, sched_step, orig, pc, num_optsteps=2, guidance_max_step=T)
+
+    # the same loop with the reference's loss formulas in stock PyTorch
+    def ref_loss(act, org, fgw, bgw):
+        up = lambda a: torch.nn.functional.interpolate(a[None], (64, 64), mode='bilinear')[0]
+        a, o = up(act), up(org)
+        fg = (o[:, pc['original_y'], pc['original_x']] - a[:, pc['transformed_y'], pc['transformed_x']]).abs().mean(-1).mean()
+        bg = (o[:, pc['background_y_orig'], pc['background_x_orig']].mean(-1) - a[:, pc['background_y_trans'], pc['background_x_trans']].mean(-1)).abs().mean()
+        return fgw * fg + bgw * bg
+    schedule = make_guidance_weight_schedule(1.5, 1.25, T, "constant")
+    lat = lat0.clone()
+    for t_idx in range(T):
+        for it in range(2):
+            l = lat.detach().requires_grad_(True)
+            _, acts = net(l, t_idx)
+            fgw, bgw = schedule(t_idx, it)
+            loss = sum(ref_loss(acts[i][0], orig[i][t_idx], fgw[i], bgw[i]) for i in range(3))
+            lat = l.detach() - 0.1 * torch.autograd.grad(loss, [l])[0]
+        with torch.no_grad():
+            lat = sched_step(net(lat, t_idx)[0], t_idx, lat)
+    assert (ours - lat).abs().max() <= 2e-4 * lat.abs().max()
+    skip = guided_denoise(lat0, list(range(T)), net, sched_step, orig, pc, num_optsteps=2, guidance_max_step=T,
+                          skip_zero_weight_layers=True)
+    assert torch.equal(skip, ours) or (skip - ours).abs().max() <= 1e-6 * ours.abs().max()
+
+
+def test_identity_npz_roundtrip(dev, tmp_path):
+    """8(f) rank 3: the reference's input_image_identity.npz layout -> device-resident stacks."""
+    from diffusionhandles_b200.identity import InputImageIdentity, load_identity, save_identity
+    ident = InputImageIdentity(null_text_emb=torch.randn(5, 1, 77, 16), init_noise=torch.randn(1, 4, 64, 64),
+                               activations=[torch.randn(5, 12, 32, 32), torch.randn(5, 6, 64, 64), torch.randn(5, 3, 64, 64)],
+                               latent_image=torch.randn(1, 4, 64, 64))
+    path = str(tmp_path / "input_image_identity.npz")
+    save_identity(path, ident)
+    with np.load(path) as z:
+        assert sorted(z.files) == sorted(["null_text_emb", "init_noise", "activations1", "activations2", "activations3", "latent_image"])
+    back = load_identity(path, dev)
+    assert all(a.device.type == "cuda" for a in back.activations)
+    for a, b in zip(ident.activations, back.activations):
+        assert torch.equal(a, b.cpu())
+    assert [tuple(t.shape) for t in back.recorded(2)] == [(12, 32, 32), (6, 64, 64), (3, 64, 64)] and back.recorded(2)[0].is_contiguous()
