@@ -31,6 +31,39 @@ def normalize_depth(depth, bounds=None, return_bounds=False):
     return 255 * (depth - min_depth) / (max_depth - min_depth)
 
 
+def depth_to_mesh(depth: torch.Tensor, intrinsics: torch.Tensor, extrinsics_R: torch.Tensor = None,
+                  extrinsics_t: torch.Tensor = None, mask: torch.Tensor = None):
+    """depth_transform.py:30-71 - triangulate a depth map: one vertex per (masked) pixel (unprojected on the device),
+    two counter-clockwise triangles per 2x2 pixel block whose corners are all inside the mask, and a per-vertex
+    ``color`` attribute (x/(W-1), y/(H-1), mask flag) that the renderer carries to the target image."""
+    from .mesh import Mesh
+    if mask is not None:
+        mask = mask.view(mask.shape[-2], mask.shape[-1])
+    H, W = depth.shape[-2], depth.shape[-1]
+    verts = depth_to_world_coords(depth, intrinsics=intrinsics, extrinsics_R=extrinsics_R, extrinsics_t=extrinsics_t)
+    if mask is not None:
+        verts = verts[mask]
+    verts = verts.view(-1, 3).contiguous()
+    vert_img_coords = torch.stack(torch.meshgrid(
+        torch.linspace(0, 1, H, device=depth.device), torch.linspace(0, 1, W, device=depth.device), indexing='xy'), dim=-1)
+    if mask is not None:
+        vert_img_coords = vert_img_coords[mask]
+    vert_img_coords = vert_img_coords.view(-1, 2).contiguous()
+    if mask is not None:
+        vertex_idx = torch.cumsum(mask.view(-1), dim=0).view(H, W) - 1
+        vertex_idx[~mask] = -1
+    else:
+        vertex_idx = torch.arange(H * W, device=depth.device, dtype=torch.int64).view(H, W)
+    upper_left = torch.stack([x.reshape(-1) for x in [vertex_idx[1:, :-1], vertex_idx[:-1, 1:], vertex_idx[:-1, :-1]]], dim=-1)
+    lower_right = torch.stack([x.reshape(-1) for x in [vertex_idx[1:, :-1], vertex_idx[1:, 1:], vertex_idx[:-1, 1:]]], dim=-1)
+    faces = torch.stack([upper_left, lower_right], dim=1).view(-1, 3)
+    faces = faces[faces.min(dim=-1).values >= 0].contiguous()
+    mesh = Mesh(verts=verts, faces=faces)
+    mesh.add_vert_attribute("color", torch.cat(
+        [vert_img_coords, torch.full_like(vert_img_coords[:, [0]], fill_value=0 if mask is None else 1)], dim=-1))
+    return mesh
+
+
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise N.NativeLibraryError(

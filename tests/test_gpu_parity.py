@@ -593,3 +593,23 @@ def test_identity_npz_roundtrip(dev, tmp_path):
     for a, b in zip(ident.activations, back.activations):
         assert torch.equal(a, b.cpu())
     assert [tuple(t.shape) for t in back.recorded(2)] == [(12, 32, 32), (6, 64, 64), (3, 64, 64)] and back.recorded(2)[0].is_contiguous()
+
+
+def test_depth_to_mesh_topology(dev, K):
+    """depth_transform.py:30-71: vertex / face counts and the colour attribute of the depth-map mesh."""
+    from diffusionhandles_b200 import depth_transform as dt
+    S = 48
+    depth, bg, mask = O.synthetic_scene(S, 41)
+    m = dt.depth_to_mesh(torch.from_numpy(bg).to(dev)[None, None], K)
+    assert m.verts.shape == (S * S, 3) and m.faces.shape == (2 * (S - 1) ** 2, 3)
+    assert np.array_equal(m.verts.cpu().numpy(), O.depth_to_world_coords(bg, K_NP).reshape(-1, 3))
+    tm = torch.from_numpy(mask > 0.5).to(dev)
+    f = dt.depth_to_mesh(torch.from_numpy(depth).to(dev)[None, None], K, mask=tm[None, None])
+    n = int(mask.sum())
+    assert f.verts.shape == (n, 3) and int(f.faces.max()) < n and f.faces.min() >= 0
+    blocks = mask[:-1, :-1] * mask[1:, :-1] * mask[:-1, 1:]
+    assert f.faces.shape[0] == int(blocks.sum() + (mask[1:, :-1] * mask[1:, 1:] * mask[:-1, 1:]).sum())
+    col = f.vert_attributes["color"]
+    assert torch.all(col[:, 2] == 1) and torch.all(m.vert_attributes["color"][:, 2] == 0)
+    ys, xs = np.nonzero(mask)
+    assert np.allclose(col[:, 0].cpu().numpy(), xs / (S - 1), atol=1e-6) and np.allclose(col[:, 1].cpu().numpy(), ys / (S - 1), atol=1e-6)
