@@ -24,8 +24,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 PER_FILE = {
     "dh_geometry.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_splat.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
+    "dh_raster.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
 }
-SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_poisson.cu"]
+SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_poisson.cu", "dh_raster.cu"]
 
 
 def _nvcc() -> str:

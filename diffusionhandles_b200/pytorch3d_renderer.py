@@ -1,4 +1,5 @@
-"""Names of the reference's ``diffhandles/pytorch3d_renderer.py`` kept importable.  The classes are the vertex
-splat renderer (``renderer.SplatRenderer``); a triangle rasteriser with pytorch3d semantics is not part of this
-build (parity unpinned)."""
-from .renderer import SplatRenderer as PyTorch3DRenderer, SplatRendererArgs as PyTorch3DRendererArgs  # noqa: F401
+"""Names of the reference's ``diffhandles/pytorch3d_renderer.py`` kept importable.  ``PyTorch3DRenderer`` is the sm_100a
+hard z-buffer triangle rasteriser (``renderer.MeshRenderer``) that follows the published semantics of pytorch3d's
+MeshRasterizer for the settings the hot path uses (faces_per_pixel = 1, hard blend); pytorch3d itself is not a dependency,
+so bit parity with it is unpinned."""
+from .renderer import MeshRenderer as PyTorch3DRenderer, SplatRendererArgs as PyTorch3DRendererArgs  # noqa: F401

@@ -67,6 +67,117 @@ class SplatRendererArgs(RendererArgs):
     background_color: Tuple[float, float, float] = (0.0, 0.0, 0.0)
 
 
+def fov_scales(k11: torch.Tensor, H: int, W: int, znear: float = 0.1):
+    """NDC scales of the FoVPerspectiveCameras the reference builds (pytorch3d_renderer.py:890-913): fov from the
+    intrinsics (of the larger image side), aspect ratio 1, evaluated with torch fp32 ops like the reference."""
+    k = k11.detach().to("cpu", torch.float32)
+    if H != W:
+        k = k * (H / max(H, W))
+    fov = 2 * torch.rad2deg(torch.atan(1 / k))
+    fov = (3.141592653589793 / 180) * fov
+    tan_half = torch.tan(fov / 2)
+    max_y = tan_half * znear
+    min_y = -max_y
+    max_x = max_y * 1.0
+    min_x = -max_x
+    return float(2.0 * znear / (max_x - min_x)), float(2.0 * znear / (max_y - min_y))
+
+
+class MeshRenderer(Renderer):
+    """Hard z-buffer TRIANGLE rasteriser behind the reference's renderer interface (mesh mode).  Follows the published
+    semantics of pytorch3d's MeshRasterizer for faces_per_pixel = 1; pytorch3d itself is not
+    available, so parity with it is unpinned.  Layers: world_position, camera_position, flat_vertex_color, depth."""
+    SUPPORTED_OUTPUTS = ("world_position", "camera_position", "flat_vertex_color", "depth")
+    SUPPORTED_SCENE_ELEMENTS = ("meshes", "cameras")
+    z_near = 0.1
+
+    def __init__(self, output_names: Optional[List[str]] = None, args: "SplatRendererArgs" = None):
+        args = SplatRendererArgs() if args is None else args
+        super().__init__(args=args)
+        self._scene: Dict[str, Any] = {}
+        self.fragments = None
+        self.set_output_layers(["world_position"] if output_names is None else output_names)
+
+    def update_scene(self, scene_elements: Dict[str, Any], ignore_unsupported_elements: bool = False):
+        if not ignore_unsupported_elements:
+            unsupported = set(scene_elements.keys()) - set(self.SUPPORTED_SCENE_ELEMENTS)
+            if len(unsupported) > 0:
+                raise RuntimeError(f"Unsupported scene elements for the mesh renderer: {unsupported}")
+        if "meshes" in scene_elements:
+            meshes = scene_elements["meshes"]
+            if not isinstance(meshes, list) or not all(isinstance(m, Mesh) for m in meshes):
+                raise RuntimeError("Provided meshes must be given as list of geometry.mesh.Mesh")
+        self._scene.update({k: v for k, v in scene_elements.items() if k in self.SUPPORTED_SCENE_ELEMENTS})
+
+    def set_output_layers(self, output_names: List[str]):
+        unsupported = set(output_names) - set(self.SUPPORTED_OUTPUTS)
+        if len(unsupported) > 0:
+            raise RuntimeError(f"Unsupported output channels: {unsupported}.")
+        if self.args.faces_per_pixel != 1 or self.args.blend_type != "hard":
+            raise RuntimeError("Only faces_per_pixel = 1 with hard blending is implemented")
+        self.output_names = list(output_names)
+
+    def render(self) -> Dict[str, torch.Tensor]:
+        if "meshes" not in self._scene or "cameras" not in self._scene:
+            raise RuntimeError("The scene needs 'meshes' and 'cameras' before rendering.")
+        lib = N.load()
+        res = self.args.output_res
+        H, W = (res, res) if isinstance(res, int) else (int(res[0]), int(res[1]))
+        meshes: List[Mesh] = self._scene["meshes"]
+        dev = meshes[0].verts.device
+        verts = torch.cat([m.verts.detach().to(torch.float32) for m in meshes], dim=0).contiguous()
+        offs, faces = 0, []
+        for m in meshes:        # join_meshes_as_scene: faces of later meshes are offset; earlier meshes win exact z ties
+            faces.append(m.faces.to(torch.int64) + offs)
+            offs += m.verts.shape[0]
+        faces = torch.cat(faces, dim=0).to(torch.int32).contiguous()
+        V, F, P = verts.shape[0], faces.shape[0], H * W
+        colors = None
+        if "flat_vertex_color" in self.output_names:
+            dims = {m.vert_attributes["color"].shape[-1] for m in meshes if m.has_vert_attribute("color")}
+            if len(dims) != 1:
+                raise RuntimeError("Vertex attribute color has different dimensions across meshes.")
+            d = dims.pop()
+            colors = torch.cat([m.vert_attributes["color"].detach().to(torch.float32) if m.has_vert_attribute("color")
+                                else torch.zeros((m.verts.shape[0], d), device=dev) for m in meshes], dim=0).contiguous()
+        st = N.stream_handle(dev)
+        ws_bytes = int(lib.dh_raster_workspace_bytes(V, H, W))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        layers = {name: [] for name in self.output_names}
+        frags = []
+        for cam in self._scene["cameras"]:
+            sx, sy = fov_scales(cam.intrinsics[1, 1], H, W, self.z_near)
+            R = (C.c_float * 9)(*cam.extrinsics_R.detach().to("cpu", torch.float32).reshape(-1).tolist())
+            T = (C.c_float * 3)(*cam.extrinsics_t.detach().to("cpu", torch.float32).reshape(-1).tolist())
+            p2f = torch.empty((H, W), dtype=torch.int32, device=dev)
+            zbuf = torch.empty((H, W), dtype=torch.float32, device=dev)
+            bary = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            N.check(lib.dh_rasterize_meshes(N.ptr(verts), V, N.ptr(faces), F, H, W, R, T, sx, sy, float(self.args.blur_radius),
+                                            int(bool(self.args.cull_backfaces)), int(bool(self.args.perspective_correct)),
+                                            int(bool(self.args.clip_barycentric_coords)), N.ptr(p2f), N.ptr(zbuf), N.ptr(bary),
+                                            N.ptr(ws), ws_bytes, st), "dh_rasterize_meshes")
+            frags.append((p2f, zbuf, bary))
+
+            def interp(attr):
+                out = torch.empty((H, W, attr.shape[1] + 1), dtype=torch.float32, device=dev)
+                N.check(lib.dh_interpolate_face_attributes(N.ptr(attr), attr.shape[1], N.ptr(faces), N.ptr(p2f), N.ptr(bary), H, W,
+                                                           N.ptr(out), st), "dh_interpolate_face_attributes")
+                return out
+            if "world_position" in layers:
+                layers["world_position"].append(interp(verts))
+            if "camera_position" in layers or "depth" in layers:
+                vcam = (verts @ cam.extrinsics_R.to(dev, torch.float32) + cam.extrinsics_t.to(dev, torch.float32)).contiguous()
+                cp = interp(vcam)
+                if "camera_position" in layers:
+                    layers["camera_position"].append(cp)
+                if "depth" in layers:
+                    layers["depth"].append(cp[..., [2, 3]].contiguous())
+            if "flat_vertex_color" in layers:
+                layers["flat_vertex_color"].append(interp(colors))
+        self.fragments = frags
+        return {k: torch.stack(v, dim=0) for k, v in layers.items()}
+
+
 class SplatRenderer(Renderer):
     SUPPORTED_OUTPUTS = ("world_position", "flat_vertex_color", "depth")
     SUPPORTED_SCENE_ELEMENTS = ("meshes", "cameras")

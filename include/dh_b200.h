@@ -249,6 +249,19 @@ int dh_poisson_fill_source(const float* image, const uint32_t* mask_a_bits, cons
                            const float* lap_source, int B, int H, int W, float* out, int max_iter, double rel_tol,
                            int32_t* iters_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- row 11 / 8(f) rank 2: hard z-buffer triangle rasteriser (mesh mode), depth_transform.py:91-195 via ------------
+ * pytorch3d_renderer.py:541-941.  Semantics of pytorch3d's rasterize_meshes for faces_per_pixel = 1 (PARITY UNPINNED:
+ * pytorch3d is not available).  verts (V,3) fp32 world space; faces (F,3) int32; view = X R + T; NDC = (sx X/Z, sy Y/Z).
+ * Outputs per pixel: pix_to_face int32 (-1 = empty), zbuf, bary (H,W,3) (clipped, perspective corrected; -1 = empty). */
+size_t dh_raster_workspace_bytes(int V, int H, int W);
+int dh_rasterize_meshes(const float* verts, int V, const int32_t* faces, int F, int H, int W,
+                        const float* R_host9, const float* T_host3, float sx, float sy, float blur_radius,
+                        int cull_backfaces, int perspective_correct, int clip_barycentric,
+                        int32_t* pix_to_face, float* zbuf, float* bary, void* ws, size_t ws_bytes, void* stream);
+/* out (H,W,D+1) = hard blend of the barycentrically interpolated vertex attribute attr (V,D), alpha last, background 0 */
+int dh_interpolate_face_attributes(const float* attr, int D, const int32_t* faces, const int32_t* pix_to_face,
+                                   const float* bary, int H, int W, float* out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

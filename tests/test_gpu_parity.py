@@ -613,3 +613,73 @@ def test_depth_to_mesh_topology(dev, K):
     assert torch.all(col[:, 2] == 1) and torch.all(m.vert_attributes["color"][:, 2] == 0)
     ys, xs = np.nonzero(mask)
     assert np.allclose(col[:, 0].cpu().numpy(), xs / (S - 1), atol=1e-6) and np.allclose(col[:, 1].cpu().numpy(), ys / (S - 1), atol=1e-6)
+
+
+def _np_depth_mesh_faces(mask):
+    """faces of depth_to_mesh (depth_transform.py:50-61) in NumPy."""
+    H, W = mask.shape
+    idx = np.cumsum(mask.reshape(-1)).reshape(H, W) - 1
+    idx[~mask] = -1
+    ul = np.stack([idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[:-1, :-1].ravel()], -1)
+    lr = np.stack([idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()], -1)
+    f = np.stack([ul, lr], 1).reshape(-1, 3)
+    return f[f.min(-1) >= 0]
+
+
+@pytest.mark.parametrize("S,seed,angle,t", [(32, 51, 35.0, (0.2, 0.0, 0.1)), (40, 52, -50.0, (-0.3, 0.1, 0.4)), (24, 53, 80.0, (0.6, 0.0, 0.5))])
+def test_triangle_rasteriser_vs_oracle(dev, K, S, seed, angle, t):
+    """Mesh mode (row 11 / 8(f) rank 2): the CUDA triangle rasteriser against the NumPy restatement of pytorch3d's
+    published rasterize_meshes semantics - pix_to_face, zbuf and barycentrics bit-exact (parity with pytorch3d itself is
+    unpinned: it is not installed and the reference has no test that pins it)."""
+    import diffusionhandles_b200 as pkg
+    pkg.install_as_diffhandles()
+    from diffhandles import depth_transform as dt
+    from diffhandles.pytorch3d_renderer import PyTorch3DRenderer, PyTorch3DRendererArgs
+    from diffhandles.renderer import Camera
+    depth, bg, mask = O.synthetic_scene(S, seed)
+    td, tb = torch.from_numpy(depth).to(dev)[None, None], torch.from_numpy(bg).to(dev)[None, None]
+    tm = torch.from_numpy(mask > 0.5).to(dev)[None, None]
+    bg_mesh = dt.depth_to_mesh(tb, K)
+    fg_mesh = dt.depth_to_mesh(td, K, mask=tm)
+    fg_mesh.verts = dt.transform_points(fg_mesh.verts, torch.tensor(angle), torch.tensor([0.0, 1.0, 0.0]), torch.tensor(t))
+    r = PyTorch3DRenderer(['world_position', 'flat_vertex_color'],
+                          PyTorch3DRendererArgs(device=dev, output_res=(S, S), cull_backfaces=True, blur_radius=1e-5))
+    r.update_scene({'meshes': [bg_mesh, fg_mesh], 'cameras': [Camera(intrinsics=K)]})
+    out = r.render()
+    p2f, zbuf, bary = (x.cpu().numpy() for x in r.fragments[0])
+    verts = torch.cat([bg_mesh.verts, fg_mesh.verts]).cpu().numpy()
+    m = mask > 0.5
+    faces = np.concatenate([_np_depth_mesh_faces(np.ones_like(m)), _np_depth_mesh_faces(m) + S * S])
+    assert np.array_equal(torch.cat([bg_mesh.faces, fg_mesh.faces + S * S]).cpu().numpy(), faces)
+    sx, sy = O.fov_scales(float(K_NP[1, 1]), S, S)
+    o_p2f, o_z, o_b = O.rasterize_meshes(verts, faces, S, S, sx, sy, 1e-5, True, True, True)
+    assert (o_p2f >= 0).all()                                   # the background mesh covers the image
+    assert (o_p2f >= 2 * (S - 1) ** 2).sum() > 10               # and the moved foreground is visible
+    assert np.array_equal(p2f, o_p2f)
+    assert np.array_equal(zbuf, o_z) and np.array_equal(bary, o_b)
+    colors = torch.cat([bg_mesh.vert_attributes["color"], fg_mesh.vert_attributes["color"]]).cpu().numpy()
+    assert np.array_equal(out['world_position'][0].cpu().numpy(), O.interpolate_face_attributes(verts, faces, o_p2f, o_b))
+    assert np.array_equal(out['flat_vertex_color'][0].cpu().numpy(), O.interpolate_face_attributes(colors, faces, o_p2f, o_b))
+
+
+def test_transform_depth_mesh_mode(dev, K):
+    """transform_depth(..., depth_transform_mode='mesh') end to end: output contract of depth_transform.py:91-195."""
+    from diffusionhandles_b200 import depth_transform as dt
+    S = 64
+    depth, bg, mask = O.synthetic_scene(S, 54)
+    td, tb, tm = (torch.from_numpy(a).to(dev)[None, None] for a in (depth, bg, mask))
+    disp, corr = dt.transform_depth(td, tb, tm, K, rot_angle=25.0, rot_axis=torch.tensor([0.0, 1.0, 0.0]),
+                                    translation=torch.tensor([0.2, 0.0, 0.1]), depth_transform_mode="mesh")
+    assert disp.shape == (1, 1, S, S) and disp.dtype == torch.float32 and disp.device.type == "cuda"
+    assert corr.device.type == "cpu" and corr.dtype == torch.int64 and corr.shape[1] == 4 and corr.shape[0] > 50
+    assert float(disp.min()) == 0.0 and abs(float(disp.max()) - 255.0) < 1e-3
+    c = corr.numpy()
+    assert (c >= 0).all() and (c < S).all()
+    assert np.all(np.diff(c[:, 3] * S + c[:, 2]) > 0)            # enumerated over target pixels in raster order
+    assert mask[c[:, 1], c[:, 0]].mean() > 0.95                  # sources lie on the foreground
+    # an identity edit maps (almost) every foreground pixel onto itself
+    _, c0 = dt.transform_depth(td, tb, tm, K, rot_angle=0.0, depth_transform_mode="mesh")
+    c0 = c0.numpy()
+    assert np.abs(c0[:, 0] - c0[:, 2]).max() <= 1 and np.abs(c0[:, 1] - c0[:, 3]).max() <= 1
+    d2, c2 = dt.transform_depth(td, tb, torch.zeros_like(tm), K, depth_transform_mode="mesh")
+    assert c2.shape == (0, 4)

@@ -185,3 +185,25 @@ def test_solve_laplacian_depth_golden(golden_small, tag):
     assert np.array_equal(np.packbits(dil), g[f"sld_{tag}/dilated"])
     sol = O.solve_laplacian_depth(depth, bg, dil)
     assert sol.dtype == np.float32 and np.array_equal(sol, g[f"sld_{tag}/solution"])
+
+
+def test_oracle_rasteriser_sanity():
+    """Mesh mode oracle (parity unpinned): a front-facing depth-map mesh covers every pixel, interpolated z is the plane
+    depth, a back-facing copy is culled, and exact z ties go to the lower face index."""
+    S = 12
+    depth = np.full((S, S), 3.0, np.float32)
+    v = O.depth_to_world_coords(depth, K).reshape(-1, 3)
+    idx = np.arange(S * S).reshape(S, S)
+    ul = np.stack([idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[:-1, :-1].ravel()], -1)
+    lr = np.stack([idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()], -1)
+    faces = np.stack([ul, lr], 1).reshape(-1, 3)
+    sx, sy = O.fov_scales(float(K[1, 1]), S, S)
+    p2f, z, b = O.rasterize_meshes(v, faces, S, S, sx, sy, 1e-5, True)
+    assert (p2f >= 0).all() and np.abs(z - 3.0).max() < 1e-5 and np.abs(b.sum(-1) - 1).max() < 1e-5
+    p2f_back, _, _ = O.rasterize_meshes(v, faces[:, ::-1], S, S, sx, sy, 1e-5, True)
+    assert (p2f_back < 0).all()
+    both = np.concatenate([faces, faces])                      # duplicated mesh: every pixel is an exact z tie
+    p2f2, _, _ = O.rasterize_meshes(v, both, S, S, sx, sy, 1e-5, True)
+    assert np.array_equal(p2f2, p2f)
+    wp = O.interpolate_face_attributes(v, faces, p2f, b)
+    assert wp.shape == (S, S, 4) and (wp[..., 3] == 1).all() and np.abs(wp[..., 2] - 3.0).max() < 1e-5
