@@ -144,9 +144,9 @@ def rigid_transform_fg(p: np.ndarray, axis: Sequence[float], angle_degrees: floa
         ((a[2] * q[:, 0]).astype(f32) - (a[0] * q[:, 2]).astype(f32)).astype(f32),
         ((a[0] * q[:, 1]).astype(f32) - (a[1] * q[:, 0]).astype(f32)).astype(f32)], axis=-1)
     # dot32: fma(q2,a2, fma(q0,a0, q1*a1)); exact (order independent) for a single-non-zero axis (A.2 caveat)
-    d = (f64(q[:, 1]) * f64(a[1])).astype(f32)
-    d = (f64(q[:, 0]) * f64(a[0]) + f64(d)).astype(f32)
-    d = (f64(q[:, 2]) * f64(a[2]) + f64(d)).astype(f32)
+    d = (q[:, 1].astype(f64) * f64(a[1])).astype(f32)
+    d = (q[:, 0].astype(f64) * f64(a[0]) + d.astype(f64)).astype(f32)
+    d = (q[:, 2].astype(f64) * f64(a[2]) + d.astype(f64)).astype(f32)
     t3 = (a[None, :] * d[:, None]).astype(f32)
     r = (q.astype(f64) * c + cr.astype(f64) * s) + t3.astype(f64) * (1 - c)
     r = (r + cen.astype(f64)) + np.array([t[0], t[1], t[2]], dtype=f64)

@@ -422,7 +422,7 @@ def test_splat_renderer_interface(dev, K):
     import diffusionhandles_b200 as pkg
     pkg.install_as_diffhandles()
     from diffhandles.renderer import Camera, Renderer
-    from diffhandles.pytorch3d_renderer import PyTorch3DRenderer, PyTorch3DRendererArgs
+    from diffusionhandles_b200.renderer import SplatRenderer, SplatRendererArgs
     from diffhandles.mesh import Mesh
     from diffhandles import depth_transform as dt
     S = 96
@@ -434,8 +434,8 @@ def test_splat_renderer_interface(dev, K):
     mb, mf = Mesh(bgp, faces), Mesh(fgp, faces)
     mb.add_vert_attribute("color", torch.cat([torch.rand(bgp.shape[0], 2, device=dev), torch.zeros(bgp.shape[0], 1, device=dev)], 1))
     mf.add_vert_attribute("color", torch.cat([torch.rand(fgp.shape[0], 2, device=dev), torch.ones(fgp.shape[0], 1, device=dev)], 1))
-    r = PyTorch3DRenderer(output_names=['world_position', 'flat_vertex_color'],
-                          args=PyTorch3DRendererArgs(device=dev, output_res=(S, S), cull_backfaces=True, blur_radius=1e-5))
+    r = SplatRenderer(output_names=['world_position', 'flat_vertex_color'],
+                      args=SplatRendererArgs(device=dev, output_res=(S, S), cull_backfaces=True, blur_radius=1e-5))
     assert isinstance(r, Renderer)
     r.update_scene(scene_elements={'meshes': [mb, mf], 'cameras': [Camera(intrinsics=K)]})
     out = r.render()
@@ -683,3 +683,69 @@ def test_transform_depth_mesh_mode(dev, K):
     assert np.abs(c0[:, 0] - c0[:, 2]).max() <= 1 and np.abs(c0[:, 1] - c0[:, 3]).max() <= 1
     d2, c2 = dt.transform_depth(td, tb, torch.zeros_like(tm), K, depth_transform_mode="mesh")
     assert c2.shape == (0, 4)
+
+
+def test_edge_cases_full_mask_single_pixel_and_batch_with_empty_edit(dev, K):
+    """Ragged / extreme inputs: every pixel foreground (N = 2P points), a one-pixel foreground, and a batch whose middle
+    edit has an empty mask; each against the oracle."""
+    from diffusionhandles_b200.engine import EditEngine, make_rigid
+    S = 64
+    depth, bg, mask = O.synthetic_scene(S, 61)
+    full = np.ones_like(mask)
+    one = np.zeros_like(mask); one[40, 21] = 1.0
+    t = (0.1, 0.0, 0.05)
+    cases = [(full, 20.0), (one, -30.0)]
+    for m, angle in cases:
+        o = O.transform_depth_pc(depth, bg, m, K_NP, angle, (0, 1, 0), f32_translation(t), poisson=False)
+        eng, res = run_edit(dev, K, depth, bg, m, angle, (0, 1, 0), t, poisson=False)
+        compare_edit(eng, res, o, S)
+    # batch of three edits, the middle one without foreground
+    eng = EditEngine(dev, 3, S, S, keep_points=True)
+    masks = [mask, np.zeros_like(mask), one]
+    td = torch.from_numpy(np.stack([depth] * 3)).to(dev)
+    tb = torch.from_numpy(np.stack([bg] * 3)).to(dev)
+    tm = torch.from_numpy(np.stack(masks)).to(dev)
+    rg = [make_rigid(a, [0.0, 1.0, 0.0], list(t)) for a in (15.0, 45.0, -60.0)]
+    res = eng.run(td, tb, tm, K, rg, poisson=False)
+    assert res.n_fg_host.tolist() == [int(mask.sum()), 0, 1] and int(res.n_corr_host[1]) == 0
+    for e, (m, a) in enumerate(zip(masks, (15.0, 45.0, -60.0))):
+        if not m.any():
+            # no foreground: the z-buffer is the background splat alone
+            dm, mk, _, _, _, win = O.points_to_depth(O.depth_to_world_coords(bg, K_NP).reshape(-1, 3).astype(np.float64), K_NP, (S, S))
+            assert np.array_equal(res.winner[e].cpu().numpy().astype(np.int64), win)
+            assert not res.target_mask[e].any()
+            continue
+        o = O.transform_depth_pc(depth, bg, m, K_NP, a, (0, 1, 0), f32_translation(t), poisson=False)
+        assert np.array_equal(res.winner[e].cpu().numpy().astype(np.int64), o["winner"])
+        assert np.array_equal(res.corr[e, : int(res.n_corr_host[e])].cpu().numpy(), o["correspondences"])
+        assert np.array_equal(res.disparity_raw[e].cpu().numpy(), o["disparity_raw"])
+
+
+def test_losses_with_zero_correspondences_are_nan_like_the_reference(dev):
+    """Zero correspondences are not an error; the reference's losses are NaN (mean over an empty set), SURVEY.md 8(b)."""
+    from diffusionhandles_b200 import losses
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
+    pc = GuidedStableDiffuser().process_correspondences(torch.zeros((0, 4), dtype=torch.int64), 512, 0)
+    cur = torch.randn(4, 32, 32, device=dev, requires_grad=True)
+    orig = torch.randn(4, 32, 32, device=dev)
+    lf = losses.compute_foreground_loss(cur, orig, pc, 1, (64, 64))
+    assert torch.isnan(lf)
+    lb = losses.compute_background_loss(cur, orig, pc, 1, (64, 64))
+    assert torch.isfinite(lb)              # the background lists cover the whole grid
+    g = torch.autograd.grad(lb, cur)[0]
+    assert torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_api_accepts_cuda_axis_float64_depth_and_noncontiguous(dev, K, golden_pc):
+    from diffusionhandles_b200 import depth_transform as dt
+    meta, g = golden_pc
+    m = meta["cfg1"]
+    depth, bg, mask = O.synthetic_scene(**m["scene"])
+    wide = torch.zeros(1, 1, 512, 1024, dtype=torch.float64, device=dev)
+    wide[..., ::2] = torch.from_numpy(depth).to(dev).double()
+    td = wide[..., ::2]                                   # float64, non-contiguous view
+    assert not td.is_contiguous()
+    tb, tm = torch.from_numpy(bg).to(dev)[None, None], torch.from_numpy(mask).to(dev)[None, None]
+    disp, corr = dt.transform_depth(td, tb, tm, K, rot_angle=m["angle"], rot_axis=torch.tensor(m["axis"], device=dev),
+                                    translation=torch.tensor(m["translation"], device=dev))
+    assert np.array_equal(corr.numpy(), g["cfg1/corr"].astype(np.int64))
