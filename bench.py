@@ -66,12 +66,55 @@ def edit_recipe(n_edits: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    The timed region is only tens of milliseconds, so the sampler is an in-process NVML thread (one query every
+    ~1 ms, no start-up delay); `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.sm, self.mx, self.reasons, self._stop, self._thread, self.nvml = [], [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and all(v.strip().isdigit() for v in ids) and index < len(ids):
+            return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        try:
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                bits = int(get_reasons(self.handle))
+                for name, bit in self._REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self._thread = threading.Thread(target=self._sample_nvml, daemon=True)
+            self._thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -86,6 +129,11 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 1 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -104,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def dist_env():
@@ -117,10 +165,11 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle port of the reference path)
 # ------------------------------------------------------------------------------------------------
-def cpu_warp_sample(n_stacks: int, with_geometry: bool, seed: int = 0):
+def cpu_warp_sample(n_stacks: int, with_geometry: bool, seed: int = 0, first_edit: int = 0):
     """Times the oracle port on `n_stacks` edits of the bench workload.  Returns (gather warps/s, e2e warps/s)."""
     from oracle import dh_oracle as O
-    scenes, edits = edit_recipe(n_stacks)
+    scenes, edits = edit_recipe(first_edit + n_stacks)
+    edits = edits[first_edit:]
     K = O.get_depth_intrinsics()
     g = torch.Generator().manual_seed(seed)
     t_geo = t_gather = 0.0
@@ -151,21 +200,28 @@ def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    n = 4
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))      # the CPU arm gets every core the container allows
+    except OSError:
+        pass
+    pool = CpuPool()
+    n = 2
     for _ in range(args.warmup):
-        cpu_warp_sample(1, True)
+        pool.rate(1)
     t0 = time.perf_counter()
-    vals = [cpu_warp_sample(n, True) for _ in range(args.steps)]
+    vals = [pool.rate(n) for _ in range(args.steps)]
     dt = time.perf_counter() - t0
-    e2e = float(np.mean([v[1] for v in vals]))
-    sample = (f"per step: {n} edits of the bench workload (oracle NumPy port of transform_depth_pc + dense maps + torch CPU "
-              f"index gather of the 4-level stack), geometry included")
+    pool.close()
+    e2e = float(np.mean(vals))
+    cores = pool.workers
+    sample = (f"per step: {n} edits on each of {cores} worker processes (oracle NumPy port of transform_depth_pc + dense maps + "
+              f"torch CPU index gather of the 4-level stack), geometry included; value = edits of the whole pool / wall time")
     line = {"impl": "reference", "metric": METRIC, "value": e2e, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config2: full SD2-depth activation stack (64^2x320,32^2x640,16^2x1280,8^2x1280) per edit, "
                                    "512^2 depth, config-4 edit recipe"},
-            "cpu_baseline": {"value": e2e, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": e2e, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -223,7 +279,7 @@ def time_kernel_steps(fn, steps: int, warmup: int, dev):
 def run_ours(args):
     import torch.distributed as dist
     from diffusionhandles_b200 import warp, _native
-    from diffusionhandles_b200.batch import EditWarpPipeline
+    from diffusionhandles_b200.batch import EditWarpPipeline, bind_host_to_gpu_numa_node
     rank, world, local = dist_env()
     if world != args.gpus and not (world == 1 and args.gpus == 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
@@ -233,6 +289,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _native.load()
+    # host threads + pinned staging buffers on the GPU's own NUMA node (matters for the e2e leg at N > 1)
+    full_affinity = os.sched_getaffinity(0)
+    host_binding = bind_host_to_gpu_numa_node(dev) if os.environ.get("DH_BENCH_NUMA_BIND", "1") == "1" else None
     n_edits = EDITS_PER_GPU
     wl = build_workload(dev, n_edits, full_map=True)
     gen = torch.Generator(device=dev).manual_seed(2 + rank)
@@ -343,9 +402,18 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        n_cpu = 24
+        os.sched_setaffinity(0, full_affinity)        # the CPU baseline gets every host core again
         cpu_warp_sample(1, True)
-        cpu_gather, cpu_e2e = cpu_warp_sample(n_cpu, True)
+        cpu_gather, cpu_serial = cpu_warp_sample(8, True)
+        cpu_cores, cpu_e2e, per_worker = 1, cpu_serial, 0
+        if world == 1:                                # BASELINE: the CPU leg runs on rank 0 at N=1 only
+            try:
+                pool = CpuPool()
+                per_worker = 4
+                cpu_e2e, cpu_cores = pool.rate(per_worker), pool.workers
+                pool.close()
+            except Exception as exc:                   # noqa: BLE001 - the serial figure stands
+                print(f"[bench] CPU pool unavailable ({exc}); reporting the single-process figure", file=sys.stderr)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,11 +426,13 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                          "kernel": "warp_dense_tma_kernel", "ms_per_launch": k3_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WARP * n_edits},
-            "cpu_baseline": {"value": cpu_e2e, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{n_cpu} edits of the same workload: oracle NumPy port of transform_depth_pc + dense maps + "
-                                       f"torch CPU index gather of the 4-level stack (gather alone: {cpu_gather:.1f} warps/s)"},
+            "cpu_baseline": {"value": cpu_e2e, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                             "sample": f"{per_worker} edits on each of {cpu_cores} worker processes of the same workload: oracle NumPy "
+                                       f"port of transform_depth_pc + dense maps + torch CPU index gather of the 4-level stack "
+                                       f"(one process alone: {cpu_serial:.1f} warps/s; its gather alone: {cpu_gather:.1f} warps/s)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_edit() * n_edits,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_edit() * n_edits, "steps": e2e_steps,
+                    "host_numa_binding": host_binding,
                     "what": "pinned host depth/mask/stack -> K1,K2,masks,correspondences,maps,K3 -> pinned host warped stack"},
             "gpu_launches": args.steps,
             "clocks": clocks,
@@ -374,6 +444,36 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _cpu_worker(job):
+    """One host process of the CPU pool: `n` edits starting at `first`, single-threaded torch."""
+    first, n = job
+    torch.set_num_threads(1)
+    cpu_warp_sample(n, True, seed=first, first_edit=first)
+    return n
+
+
+class CpuPool:
+    """The reference path is single-threaded Python/NumPy, but edits are independent: to give the CPU arm every
+    host thread, one worker process per available core each runs its own edits (spawned, so no CUDA/OpenMP state
+    is inherited).  `rate(k)` = edits/s of the whole pool on k edits per worker."""
+
+    def __init__(self, workers: int = 0):
+        import multiprocessing as mp
+        self.workers = workers or min(len(os.sched_getaffinity(0)), 64)     # bounded: each worker imports torch
+        self.pool = mp.get_context("spawn").Pool(self.workers)
+        self.pool.map(_cpu_worker, [(0, 1)] * self.workers)           # import + first-call costs outside the timing
+
+    def rate(self, edits_per_worker: int) -> float:
+        jobs = [(w * edits_per_worker, edits_per_worker) for w in range(self.workers)]
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_cpu_worker, jobs, chunksize=1))
+        return done / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pool.terminate()
+        self.pool.join()
 
 
 def main():

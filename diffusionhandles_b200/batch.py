@@ -25,6 +25,33 @@ def shard_edits(n_edits: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, n_edits, world_size))
 
 
+def bind_host_to_gpu_numa_node(device) -> Optional[dict]:
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned staging buffers
+    allocated afterwards are node-local (first touch) and H2D/D2H DMA does not cross the socket interconnect.
+    Call before allocating pinned memory.  Returns {'numa_node', 'cpus'} or None when the topology is not visible
+    (containers without sysfs NUMA information); never raises."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 class EditWarpPipeline:
     def __init__(self, device: torch.device, S: int, level_shapes: Sequence[Tuple[int, int]], chunk: int = 16,
                  n_streams: int = 3, full_winner_map: bool = True):
