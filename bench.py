@@ -329,7 +329,7 @@ def run_ours(args):
     value = world * n_edits * args.steps / (total_ms * 1e-3)
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----
-    per_launch = time_kernel_steps(step, max(args.steps, 10), 3, dev)
+    per_launch = time_kernel_steps(step, max(args.steps, 100), 3, dev)   # >= 100 launches: ~75 ms under load for the clock sampler
     clocks = sampler.stop()          # sampled over the K timed steps and the per-launch roofline loop
     k3_ms = float(np.mean(per_launch))
     achieved = ALGO_BYTES_PER_WARP * n_edits / (k3_ms * 1e-3) / 1e9
