@@ -80,6 +80,9 @@ _SIGNATURES = {
     "dh_warp_gather_list": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dh_warp_gather_dense": (c_int, [C.POINTER(dh_warp_level), c_int, c_int, c_void_p]),
     "dh_guidance_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dh_guidance_loss_patch_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dh_guidance_loss_patch": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_loss_resize_tables_bytes": (c_size_t, []),
     "dh_build_loss_resize_tables": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dh_loss_plan_bytes": (c_size_t, [c_int, c_int]),

@@ -26,7 +26,7 @@ PER_FILE = {
     "dh_splat.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_raster.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
 }
-SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_poisson.cu", "dh_raster.cu"]
+SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_loss_patch.cu", "dh_poisson.cu", "dh_raster.cu"]
 
 
 def _nvcc() -> str:

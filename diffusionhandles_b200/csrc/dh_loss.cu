@@ -20,47 +20,11 @@
 //     out of the same pass: algorithmic traffic = read cur + read orig + write grad.
 //     A tiny second kernel reduces the per-channel partial sums in a fixed order.
 #include "dh_common.cuh"
+#include "dh_loss_plan.cuh"
 
 #include <string.h>
 
 namespace dh {
-
-constexpr int kMaxLossLayers = 8;
-constexpr int kMaxG = 64;
-constexpr int kMaxNative = 64;
-
-struct PlanHeader {
-    int32_t n_pairs, n_fg, n_bg_orig, n_bg_trans, n_bg_common, grid, cap, reserved;
-    int32_t box_r0, box_r1, box_s0, box_s1;   // box (loss-grid rows / columns) of the cells that are a pair source or destination
-};
-
-struct PlanView {
-    PlanHeader* hdr;
-    int32_t* row_ptr;      // cells + 1
-    ushort4* bgcnt;        // cells: (count in bg_orig, bg_trans, bg_common, bit0 = cell is the source of a pair)
-    uint2* pairs;          // cap entries: x = src | dst << 16, y = multiplicity
-};
-
-__host__ __device__ inline size_t plan_layout(int grid, int cap, size_t* o_row, size_t* o_bg, size_t* o_pairs) {
-    const size_t cells = (size_t)grid * grid;
-    size_t o = sizeof(PlanHeader);
-    *o_row = o;   o += ((cells + 1) * sizeof(int32_t) + 15) / 16 * 16;
-    *o_bg = o;    o += cells * sizeof(ushort4);
-    *o_pairs = o; o += ((size_t)(cap > 0 ? cap : 1) * sizeof(uint2) + 15) / 16 * 16;
-    return o;
-}
-
-__host__ __device__ inline PlanView plan_view(void* plan, int grid, int cap) {
-    size_t a, b, c;
-    plan_layout(grid, cap, &a, &b, &c);
-    char* p = static_cast<char*>(plan);
-    PlanView v;
-    v.hdr = reinterpret_cast<PlanHeader*>(p);
-    v.row_ptr = reinterpret_cast<int32_t*>(p + a);
-    v.bgcnt = reinterpret_cast<ushort4*>(p + b);
-    v.pairs = reinterpret_cast<uint2*>(p + c);
-    return v;
-}
 
 // ------------------------------------------------------------------------------------------------
 // plan builder: one CTA of 1024 threads
@@ -247,16 +211,6 @@ __device__ __forceinline__ int layer_of(const LossParams& p, int gc) {
     return l;
 }
 
-// torch area_pixel_compute_source_index (align_corners = False) for output index i
-__device__ __forceinline__ void bilinear_tap(int i, int n_in, float scale, int& i0, int& i1, float& lam) {
-    float src = scale * ((float)i + 0.5f) - 0.5f;
-    src = src < 0.0f ? 0.0f : src;
-    i0 = (int)src;
-    if (i0 > n_in - 1) i0 = n_in - 1;
-    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
-    lam = src - (float)i0;
-}
-
 // sum over the CTA of three values, result in every thread; fixed order (warp tree, then a tree over the warp
 // partials that every warp evaluates identically) -> deterministic.  One barrier.
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*red)[4]) {
@@ -322,7 +276,6 @@ __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ float sgn(float d) { return d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f); }
 
 // ---- layers at the loss-grid resolution -------------------------------------------------------------
 template <bool kBinary>
@@ -358,9 +311,10 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid
     };
     if (tid < p.n_layers) {
         const LossLayerDev& L = p.lv[tid];
-        lconst[tid][0] = p.fg_kind ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
-        lconst[tid][1] = p.bg_kind == 2 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
-        lconst[tid][2] = p.bg_kind == 1 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
+        // an empty index list makes the reference's loss NaN (mean over nothing) but its gradient ZERO: scale 0, not inf
+        lconst[tid][0] = p.fg_kind && p.n_fg > 0 ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
+        lconst[tid][1] = p.bg_kind == 2 && p.n_bg_common > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
+        lconst[tid][2] = p.bg_kind == 1 && p.n_bg_trans > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
     }
     const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
     __syncthreads();
@@ -570,9 +524,10 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __gr
 
     if (tid < p.n_layers) {
         const LossLayerDev& L = p.lv[tid];
-        sh.lconst[tid][0] = p.fg_kind ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
-        sh.lconst[tid][1] = p.bg_kind == 2 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
-        sh.lconst[tid][2] = p.bg_kind == 1 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
+        // an empty index list makes the reference's loss NaN (mean over nothing) but its gradient ZERO: scale 0, not inf
+        sh.lconst[tid][0] = p.fg_kind && p.n_fg > 0 ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
+        sh.lconst[tid][1] = p.bg_kind == 2 && p.n_bg_common > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
+        sh.lconst[tid][2] = p.bg_kind == 1 && p.n_bg_trans > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
     }
     const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
     // the active box is a property of the plan (identical in every layer's table)

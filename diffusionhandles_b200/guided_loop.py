@@ -26,8 +26,6 @@ def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, s
 
     guided_stable_diffuser.py:415-434: loss = sum_l fgw[l] * L_fg,l + bgw[l] * L_bg,l; latents -= 0.1 * dloss/dlatents.
     """
-    if fg_patch_size != 1 or bg_patch_size != 1:
-        raise NotImplementedError("patch sizes > 1 are not implemented (every shipped config uses 1)")
     schedule = make_guidance_weight_schedule(fg_weight, bg_weight, guidance_max_step, guidance_schedule_type)
     for t_idx, t in enumerate(timesteps):
         iteration = 0
@@ -46,7 +44,8 @@ def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, s
                     fgw, bgw = [fgw[i] for i in keep], [bgw[i] for i in keep]
                 if acts:
                     loss, _ = guidance_loss(acts, origs, processed_correspondences, fgw, bgw, bg_loss_type=bg_loss_type,
-                                            activations_size=activations_size)
+                                            activations_size=activations_size, patch_size=fg_patch_size,
+                                            bg_patch_size=bg_patch_size)
                     grad = torch.autograd.grad(loss, [lat])[0]
                     latents = lat.detach() - grad * step_size
             iteration += 1

@@ -103,14 +103,14 @@ def _as_f32(t: torch.Tensor, dev) -> torch.Tensor:
 
 def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_grad: Sequence[bool],
             fgw: Sequence[float], bgw: Sequence[float], plan: LossPlan, fg_kind: int,
-            bg_kind: int) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+            bg_kind: int, patch: int = 1) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
     lib = N.load()
     dev = curs[0].device
     if dev.type != "cuda":
         raise N.NativeLibraryError("guidance losses run on CUDA only; there is no CPU fallback")
     L = len(curs)
     shapes = tuple(tuple(c.shape) for c in curs)
-    key = (shapes, fg_kind, bg_kind)
+    key = (shapes, fg_kind, bg_kind, patch)
     runner = plan._runners.get(key)
     if runner is None:
         # per (plan, shapes): the ctypes layer array, the workspace and the resize tables are created once
@@ -121,10 +121,15 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         tabs = []
         for i, sh in enumerate(shapes):
             layers[i].channels, layers[i].h, layers[i].w = sh
-            t = None if (sh[1], sh[2]) == (plan.grid, plan.grid) else plan.resize_tables(sh[1], sh[2], fg_kind, bg_kind)
+            if sh[1] > plan.grid or sh[2] > plan.grid:
+                raise NotImplementedError(f"activation maps larger than the loss grid ({sh[1]}x{sh[2]} > {plan.grid}) are not implemented")
+            t = None
+            if patch == 1 and (sh[1], sh[2]) != (plan.grid, plan.grid):
+                t = plan.resize_tables(sh[1], sh[2], fg_kind, bg_kind)
             tabs.append(t)
             layers[i].resize_tables = N.ptr(t) if t is not None else None
-        ws_bytes = int(lib.dh_guidance_loss_workspace_bytes(L, max(sh[0] for sh in shapes)))
+        ws_fn = lib.dh_guidance_loss_workspace_bytes if patch == 1 else lib.dh_guidance_loss_patch_workspace_bytes
+        ws_bytes = int(ws_fn(L, max(sh[0] for sh in shapes)))
         runner = (layers, torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes, tabs)
         plan._runners[key] = runner
     layers, ws, ws_bytes, _ = runner
@@ -142,9 +147,13 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
     n_fg, n_bo, n_bt, n_bc = plan.n
-    N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
-                                 fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes,
-                                 torch.cuda.current_stream(dev).cuda_stream), "dh_guidance_loss")
+    st = torch.cuda.current_stream(dev).cuda_stream
+    if patch == 1:
+        N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
+                                     fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
+    else:
+        N.check(lib.dh_guidance_loss_patch(layers, L, plan.grid, patch, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind,
+                                           out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss_patch")
     return out, grads
 
 
@@ -154,7 +163,8 @@ class _FusedLoss(torch.autograd.Function):
         L = spec["L"]
         curs, origs = acts[:L], acts[L:]
         want = [ctx.needs_input_grad[1 + i] for i in range(L)]
-        out, grads = _launch(curs, origs, want, spec["fgw"], spec["bgw"], spec["plan"], spec["fg_kind"], spec["bg_kind"])
+        out, grads = _launch(curs, origs, want, spec["fgw"], spec["bgw"], spec["plan"], spec["fg_kind"], spec["bg_kind"],
+                             spec.get("patch", 1))
         ctx.grads = grads
         ctx.n_inputs = len(acts)
         total, parts = out[0].clone(), out[1:].clone()
@@ -178,6 +188,19 @@ class _FusedLoss(torch.autograd.Function):
         return tuple(res)
 
 
+_MAX_PATCH = 31
+
+
+def _patch_of(patch_size) -> int:
+    """patch_size of the local-average losses (losses.py:64: AvgPool2d(patch_size, stride=1, padding=patch_size//2))."""
+    p = int(patch_size)
+    if p < 1 or p != patch_size:
+        raise ValueError(f"patch_size must be a positive integer, got {patch_size!r}")
+    if p > _MAX_PATCH:
+        raise NotImplementedError(f"patch_size > {_MAX_PATCH} is not implemented (every shipped config uses 1)")
+    return p
+
+
 def _grid_of(activations_size) -> int:
     hs, ws = int(activations_size[0]), int(activations_size[1])
     if hs != ws:
@@ -187,26 +210,36 @@ def _grid_of(activations_size) -> int:
 
 def guidance_loss(activations: Sequence[torch.Tensor], activations_orig: Sequence[torch.Tensor], processed_correspondences,
                   fg_weights: Sequence[float], bg_weights: Sequence[float], bg_loss_type: str = 'global_avg',
-                  activations_size=(64, 64), patch_size: int = 1):
+                  activations_size=(64, 64), patch_size: int = 1, bg_patch_size: Optional[int] = None):
     """sum_l fgw[l]*compute_foreground_loss(l) + bgw[l]*compute_background_loss(l) in ONE fused launch
-    (guided_stable_diffuser.py:417-428).  Returns (total 0-d tensor, per-term values (2L,) tensor)."""
-    if patch_size != 1:
-        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    (guided_stable_diffuser.py:417-428).  Returns (total 0-d tensor, per-term values (2L,) tensor: fg_0, bg_0, fg_1, ...).
+    ``patch_size`` is the foreground patch (fg_patch_size), ``bg_patch_size`` the background one (defaults to the same);
+    when the two differ the foreground and the background terms take one launch each."""
     if bg_loss_type not in ('global_avg', 'local_avg'):
         raise ValueError(f'Unknown background loss type: {bg_loss_type}')
     grid = _grid_of(activations_size)
     dev = activations[0].device
-    spec = dict(L=len(activations), fgw=list(fg_weights), bgw=list(bg_weights), plan=_plan_for(processed_correspondences, grid, dev),
-                fg_kind=_FG, bg_kind=_BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL)
-    return _FusedLoss.apply(spec, *activations, *activations_orig)
+    fg_patch = _patch_of(patch_size)
+    bg_patch = _patch_of(patch_size if bg_patch_size is None else bg_patch_size) if bg_loss_type == 'local_avg' else fg_patch
+    plan = _plan_for(processed_correspondences, grid, dev)
+    bg_kind = _BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL
+    L = len(activations)
+    if fg_patch == bg_patch:
+        spec = dict(L=L, fgw=list(fg_weights), bgw=list(bg_weights), plan=plan, fg_kind=_FG, bg_kind=bg_kind, patch=fg_patch)
+        return _FusedLoss.apply(spec, *activations, *activations_orig)
+    zeros = [0.0] * L
+    fg_total, fg_parts = _FusedLoss.apply(dict(L=L, fgw=list(fg_weights), bgw=zeros, plan=plan, fg_kind=_FG, bg_kind=0, patch=fg_patch),
+                                          *activations, *activations_orig)
+    bg_total, bg_parts = _FusedLoss.apply(dict(L=L, fgw=zeros, bgw=list(bg_weights), plan=plan, fg_kind=0, bg_kind=bg_kind, patch=bg_patch),
+                                          *activations, *activations_orig)
+    return fg_total + bg_total, fg_parts + bg_parts
 
 
 def compute_foreground_loss(activations, activations_orig, processed_correspondences, patch_size, activations_size):
     """losses.py:4-17."""
-    if patch_size != 1:
-        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
     grid = _grid_of(activations_size)
-    spec = dict(L=1, fgw=[1.0], bgw=[0.0], plan=_plan_for(processed_correspondences, grid, activations.device), fg_kind=_FG, bg_kind=0)
+    spec = dict(L=1, fgw=[1.0], bgw=[0.0], plan=_plan_for(processed_correspondences, grid, activations.device), fg_kind=_FG, bg_kind=0,
+                patch=_patch_of(patch_size))
     return _FusedLoss.apply(spec, activations, activations_orig)[0]
 
 
@@ -215,11 +248,10 @@ def compute_background_loss(activations, activations_orig, processed_corresponde
     """losses.py:19-40."""
     if loss_type not in ('global_avg', 'local_avg'):
         raise ValueError(f'Unknown background loss type: {loss_type}')
-    if loss_type == 'local_avg' and patch_size != 1:
-        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
     grid = _grid_of(activations_size)
     spec = dict(L=1, fgw=[0.0], bgw=[1.0], plan=_plan_for(processed_correspondences, grid, activations.device),
-                fg_kind=0, bg_kind=_BG_GLOBAL if loss_type == 'global_avg' else _BG_LOCAL)
+                fg_kind=0, bg_kind=_BG_GLOBAL if loss_type == 'global_avg' else _BG_LOCAL,
+                patch=_patch_of(patch_size) if loss_type == 'local_avg' else 1)       # 'global_avg' ignores the patch
     return _FusedLoss.apply(spec, activations, activations_orig)[0]
 
 
@@ -244,12 +276,11 @@ def average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2):
 
 
 def local_average_feat_l1_loss(feat_map_1, feat_map_2, x1, y1, x2, y2, patch_size=1):
-    """losses.py:51-84 with patch_size == 1: mean_c mean_n |f1[c,y1,x1] - f2[c,y2,x2]|."""
-    if patch_size != 1:
-        raise NotImplementedError("patch_size > 1 is not implemented (every shipped config uses 1; SURVEY.md 8(f) rank 4)")
+    """losses.py:51-84: mean_c mean_n |avg_p(f1)[c,y1,x1] - avg_p(f2)[c,y2,x2]| (avg_1 is the identity)."""
+    patch = _patch_of(patch_size)
     grid = _grid_of(feat_map_1.shape[-2:])
     dev = feat_map_2.device
     a, b = _to_cells(y1, x1, grid, dev), _to_cells(y2, x2, grid, dev)
-    fwd = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=a, fg_dst=b), fg_kind=_FG, bg_kind=0)
-    swp = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=b, fg_dst=a), fg_kind=_FG, bg_kind=0)
+    fwd = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=a, fg_dst=b), fg_kind=_FG, bg_kind=0, patch=patch)
+    swp = dict(L=1, fgw=[1.0], bgw=[0.0], plan=LossPlan(grid, dev, fg_src=b, fg_dst=a), fg_kind=_FG, bg_kind=0, patch=patch)
     return _two_sided(fwd, swp, feat_map_1, feat_map_2)

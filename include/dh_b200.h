@@ -233,6 +233,14 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
                      int fg_kind, int bg_kind,
                      float* loss_out /* device float[1 + 2*n_layers]: total, then fg_l, bg_l */,
                      void* ws, size_t ws_bytes, void* stream);
+/* The same losses with patch_size > 1 (losses.py:62-77: both maps are replaced by their local averages over the indexed
+ * cells, AvgPool2d(patch, stride 1, padding patch//2) of w*f divided by that of w plus 1e-10, before the L1 difference;
+ * 'global_avg' ignores the patch).  Same plan, layer descriptors (resize_tables unused) and loss_out layout as
+ * dh_guidance_loss; 1 <= patch_size <= 31.  patch_size == 1 gives the dh_guidance_loss result. */
+size_t dh_guidance_loss_patch_workspace_bytes(int n_layers, int max_channels);
+int dh_guidance_loss_patch(const dh_loss_layer* layers_host, int n_layers, int grid, int patch_size, const void* plan,
+                           int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind,
+                           float* loss_out, void* ws, size_t ws_bytes, void* stream);
 /* grads *= *scale (device scalar); exits early on the device when *scale == 1. */
 int dh_scale_inplace(float* data, size_t n, const float* scale, void* stream);
 

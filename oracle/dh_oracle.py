@@ -567,20 +567,57 @@ def bilinear_resize_transpose(G: np.ndarray, in_size: Tuple[int, int], dtype=f64
     return np.einsum("cyx,yh,xw->chw", G.astype(dtype), My, Mx).astype(dtype)
 
 
+def box_sum(M: np.ndarray, patch: int) -> np.ndarray:
+    """Window sums of ``AvgPool2d(patch, stride=1, padding=patch//2)`` (zero padded, losses.py:64) at the first H x W
+    output positions: out[.., q] = sum_{d in [0,patch)} M[.., q - patch//2 + d].  (For an even patch torch's output has
+    one more row and column; the losses only ever index rows/columns < H.)"""
+    C, H, W = M.shape
+    pad = patch // 2
+    Mp = np.pad(M, ((0, 0), (pad, patch), (pad, patch)))
+    out = np.zeros_like(M)
+    for dy in range(patch):
+        for dx in range(patch):
+            out = out + Mp[:, dy:dy + H, dx:dx + W]
+    return out
+
+
+def box_sum_transpose(Q: np.ndarray, patch: int) -> np.ndarray:
+    """Adjoint of ``box_sum``: out[.., j] = sum of Q over the output positions q (< H) whose window contains j."""
+    C, H, W = Q.shape
+    pad = patch // 2
+    Qp = np.pad(Q, ((0, 0), (patch, patch), (patch, patch)))
+    out = np.zeros_like(Q)
+    for dy in range(patch):
+        for dx in range(patch):
+            out = out + Qp[:, pad - dy + patch:pad - dy + patch + H, pad - dx + patch:pad - dx + patch + W]
+    return out
+
+
 def foreground_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray],
                     size=(64, 64), dtype=f64, x1="original_x", y1="original_y",
-                    x2="transformed_x", y2="transformed_y"):
-    """losses.py:4-17 + :51-84 with patch_size=1.  Returns (loss, dL/dcur at native resolution).
+                    x2="transformed_x", y2="transformed_y", patch: int = 1):
+    """losses.py:4-17 + :51-84.  Returns (loss, dL/dcur at native resolution).
 
-    L = mean_c mean_n |up(orig)[c,src_n] - up(cur)[c,dst_n]|.
-    """
+    patch 1: L = mean_c mean_n |up(orig)[c,src_n] - up(cur)[c,dst_n]|.
+    patch p: the two maps are first replaced by their local averages over the indexed cells,
+             F[c,q] = (box_p(w * up)[c,q] / p^2) / (box_p(w)[q] / p^2 + 1e-10),  w = 1 on the indexed cells
+             (losses.py:57-77), and the gradient flows back through the average of the current map.
+    An empty index list gives loss NaN (mean over nothing) and gradient ZERO, as torch's autograd does."""
     C, h, w = cur.shape
     uo = bilinear_resize(orig, size, dtype)
     uc = bilinear_resize(cur, size, dtype)
     ys, xs, yd, xd = pc[y1], pc[x1], pc[y2], pc[x2]
     N = len(xs)
     if N == 0:
-        return dtype(np.nan), np.full(cur.shape, np.nan, dtype)
+        return dtype(np.nan), np.zeros(cur.shape, dtype)
+    if patch != 1:
+        w1 = np.zeros((1,) + tuple(size), dtype); w2 = np.zeros((1,) + tuple(size), dtype)
+        w1[0, ys, xs] = 1; w2[0, yd, xd] = 1
+        pp = dtype(patch * patch)
+        den1 = (box_sum(w1, patch) / pp + dtype(1e-10)).astype(dtype)
+        den2 = (box_sum(w2, patch) / pp + dtype(1e-10)).astype(dtype)
+        uo = ((box_sum(w1 * uo, patch) / pp).astype(dtype) / den1).astype(dtype)
+        uc = ((box_sum(w2 * uc, patch) / pp).astype(dtype) / den2).astype(dtype)
     d = uo[:, ys, xs] - uc[:, yd, xd]
     loss = np.abs(d).mean(axis=-1).mean()
     g_up = np.zeros((C, size[0] * size[1]), dtype)
@@ -593,15 +630,18 @@ def foreground_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray]
         import scipy.sparse
         Sm = scipy.sparse.csr_matrix((np.ones(N), (np.arange(N), cell)), shape=(N, size[0] * size[1]))
         g_up = np.asarray(contrib @ Sm)
-    g = bilinear_resize_transpose(g_up.reshape(C, *size), (h, w), dtype)
+    g_up = g_up.reshape(C, *size)
+    if patch != 1:
+        g_up = (w2 * box_sum_transpose((g_up / den2 / pp).astype(dtype), patch)).astype(dtype)
+    g = bilinear_resize_transpose(g_up, (h, w), dtype)
     return dtype(loss), g
 
 
 def background_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray],
-                    size=(64, 64), loss_type: str = "global_avg", dtype=f64):
-    """losses.py:19-49.  Returns (loss, dL/dcur)."""
+                    size=(64, 64), loss_type: str = "global_avg", dtype=f64, patch: int = 1):
+    """losses.py:19-49.  Returns (loss, dL/dcur).  ``patch`` only matters for 'local_avg'."""
     if loss_type == "local_avg":
-        return foreground_loss(cur, orig, pc, size, dtype, "background_x", "background_y", "background_x", "background_y")
+        return foreground_loss(cur, orig, pc, size, dtype, "background_x", "background_y", "background_x", "background_y", patch)
     if loss_type != "global_avg":
         raise ValueError(f"Unknown background loss type: {loss_type}")
     C, h, w = cur.shape
@@ -609,7 +649,9 @@ def background_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray]
     uc = bilinear_resize(cur, size, dtype)
     y1, x1 = pc["background_y_orig"], pc["background_x_orig"]
     y2, x2 = pc["background_y_trans"], pc["background_x_trans"]
-    if len(x1) == 0 or len(x2) == 0:
+    if len(x2) == 0:
+        return dtype(np.nan), np.zeros(cur.shape, dtype)          # NaN loss, nothing to scatter the gradient to
+    if len(x1) == 0:
         return dtype(np.nan), np.full(cur.shape, np.nan, dtype)
     delta = uo[:, y1, x1].mean(-1) - uc[:, y2, x2].mean(-1)
     loss = np.abs(delta).mean()
@@ -619,27 +661,43 @@ def background_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray]
 
 
 def loss_sign_ambiguity(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray], size=(64, 64),
-                        bg_loss_type: str = "global_avg", eps: float = 2e-6) -> np.ndarray:
+                        bg_loss_type: str = "global_avg", eps: float = 2e-6, patch: int = 1, bg_patch: Optional[int] = None) -> np.ndarray:
     """bool (C,h,w): native cells whose gradient depends on sign(d) of a difference with |d| < eps.
 
     The losses are L1: their gradient is a sum of +-1/(C N) terms.  Where a difference is within fp32 rounding
     of zero, its sign - and with it one gradient quantum - legitimately depends on the arithmetic (fp32 vs fp64,
     FMA contraction); the reference itself differs between its CPU and CUDA runs there.  Parity tests compare the
-    gradients on the complement of this mask and require the mask to be a vanishing fraction of the tensor."""
+    gradients on the complement of this mask and require the mask to be a vanishing fraction of the tensor.
+    With a patch > 1 the difference is taken between local averages and one quantum spreads over the patch."""
     C, h, w = cur.shape
+    bg_patch = patch if bg_patch is None else bg_patch
     uo = bilinear_resize(orig, size, f64)
     uc = bilinear_resize(cur, size, f64)
-    amb_up = np.zeros((C, size[0] * size[1]), bool)
+
+    def local(ys, xs, yd, xd, p):
+        a, b = uo, uc
+        w2 = np.zeros((1,) + tuple(size), f64)
+        w2[0, yd, xd] = 1
+        if p != 1:
+            w1 = np.zeros((1,) + tuple(size), f64)
+            w1[0, ys, xs] = 1
+            a = box_sum(w1 * uo, p) / (box_sum(w1, p) + 1e-10 * p * p)
+            b = box_sum(w2 * uc, p) / (box_sum(w2, p) + 1e-10 * p * p)
+        d = a[:, ys, xs] - b[:, yd, xd]
+        amb = np.zeros((C, size[0] * size[1]), bool)
+        cc, nn = np.nonzero(np.abs(d) < eps)
+        amb[cc, (yd * size[1] + xd)[nn]] = True
+        amb = amb.reshape(C, *size)
+        if p != 1:
+            amb = (box_sum_transpose(amb.astype(f64), p) > 0) & (w2 > 0)
+        return amb
+
+    amb_up = np.zeros((C,) + tuple(size), bool)
     if len(pc["original_x"]):
-        d = uo[:, pc["original_y"], pc["original_x"]] - uc[:, pc["transformed_y"], pc["transformed_x"]]
-        cell = pc["transformed_y"] * size[1] + pc["transformed_x"]
-        cc, nn = np.nonzero(np.abs(d) < eps)
-        amb_up[cc, cell[nn]] = True
-    if bg_loss_type == "local_avg":
-        d = uo[:, pc["background_y"], pc["background_x"]] - uc[:, pc["background_y"], pc["background_x"]]
-        cc, nn = np.nonzero(np.abs(d) < eps)
-        amb_up[cc, (pc["background_y"] * size[1] + pc["background_x"])[nn]] = True
-    amb = bilinear_resize_transpose(amb_up.reshape(C, *size).astype(f64), (h, w), f64) > 0
+        amb_up |= local(pc["original_y"], pc["original_x"], pc["transformed_y"], pc["transformed_x"], patch)
+    if bg_loss_type == "local_avg" and len(pc["background_x"]):
+        amb_up |= local(pc["background_y"], pc["background_x"], pc["background_y"], pc["background_x"], bg_patch)
+    amb = bilinear_resize_transpose(amb_up.astype(f64), (h, w), f64) > 0
     if bg_loss_type == "global_avg" and len(pc["background_x_orig"]) and len(pc["background_x_trans"]):
         delta = uo[:, pc["background_y_orig"], pc["background_x_orig"]].mean(-1) - uc[:, pc["background_y_trans"], pc["background_x_trans"]].mean(-1)
         amb[np.abs(delta) < eps] = True

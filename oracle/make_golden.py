@@ -179,6 +179,21 @@ def make_small_goldens(ref):
         out[f"sld_{tag}/S_it"] = np.array([S, it])
         out[f"sld_{tag}/dilated"] = np.packbits(dil)
         out[f"sld_{tag}/solution"] = sol
+    # local-average losses with patch_size > 1 (losses.py:62-77): odd and even patches, native and resized maps,
+    # separate generator so that the fixtures above keep their values
+    rng2 = np.random.default_rng(77)
+    for tag, (C, h, patch) in {"p3c4h64": (4, 64, 3), "p5c3h32": (3, 32, 5), "p2c3h16": (3, 16, 2), "p4c2h64": (2, 64, 4)}.items():
+        cur = torch.from_numpy(rng2.normal(size=(C, h, h)).astype(np.float32)).requires_grad_(True)
+        orig = torch.from_numpy(rng2.normal(size=(C, h, h)).astype(np.float32))
+        out[f"ploss_{tag}/cur"] = cur.detach().numpy()
+        out[f"ploss_{tag}/orig"] = orig.numpy()
+        out[f"ploss_{tag}/patch"] = np.int64(patch)
+        lf = ref.losses.compute_foreground_loss(cur, orig, pc, patch, (64, 64))
+        out[f"ploss_{tag}/fg"] = lf.detach().numpy()
+        out[f"ploss_{tag}/fg_grad"] = torch.autograd.grad(lf, cur)[0].numpy()
+        lb = ref.losses.compute_background_loss(cur, orig, pc, patch, (64, 64), loss_type="local_avg")
+        out[f"ploss_{tag}/bg_local_avg"] = lb.detach().numpy()
+        out[f"ploss_{tag}/bg_local_avg_grad"] = torch.autograd.grad(lb, cur)[0].numpy()
     np.savez_compressed(os.path.join(GOLDEN_DIR, "small_cases.npz"), **out)
     print(f"[golden] small cases: {len(out)} arrays")
 

@@ -342,6 +342,91 @@ def test_losses_golden(dev, golden_small, golden_pc, tag):
         losses.compute_background_loss(cur, orig, pc, 1, (64, 64), loss_type="nope")
 
 
+@pytest.mark.parametrize("tag", ["p3c4h64", "p5c3h32", "p2c3h16", "p4c2h64"])
+def test_patch_losses_golden(dev, golden_small, golden_pc, tag):
+    """patch_size > 1 (losses.py:62-77): dh_guidance_loss_patch against values and autograd
+    gradients recorded from the reference, odd and even patches, native and resized maps; 1e-5 relative."""
+    from diffusionhandles_b200 import losses
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
+    g = golden_small
+    _, gp = golden_pc
+    pc = GuidedStableDiffuser().process_correspondences(torch.from_numpy(gp["cfg1/corr"].astype(np.int64)), 512, 0)
+    pc_np = O.process_correspondences(gp["cfg1/corr"].astype(np.int64), 512, 0)
+    cur_np, orig_np, patch = g[f"ploss_{tag}/cur"], g[f"ploss_{tag}/orig"], int(g[f"ploss_{tag}/patch"])
+    orig = torch.from_numpy(orig_np).to(dev)
+    amb = O.loss_sign_ambiguity(cur_np, orig_np, pc_np, bg_loss_type="local_avg", patch=patch)
+    assert amb.mean() < 1e-3
+    cur = torch.from_numpy(cur_np).to(dev).requires_grad_(True)
+    lf = losses.compute_foreground_loss(cur, orig, pc, patch, (64, 64))
+    gf = torch.autograd.grad(lf, cur)[0].cpu().numpy()
+    assert abs(lf.item() - g[f"ploss_{tag}/fg"]) <= 1e-5 * abs(g[f"ploss_{tag}/fg"])
+    assert np.where(amb, 0.0, np.abs(gf - g[f"ploss_{tag}/fg_grad"])).max() <= 1e-5 * np.abs(g[f"ploss_{tag}/fg_grad"]).max()
+    cur = torch.from_numpy(cur_np).to(dev).requires_grad_(True)
+    lb = losses.compute_background_loss(cur, orig, pc, patch, (64, 64), loss_type="local_avg")
+    gb = torch.autograd.grad(lb, cur)[0].cpu().numpy()
+    assert abs(lb.item() - g[f"ploss_{tag}/bg_local_avg"]) <= 1e-5 * abs(g[f"ploss_{tag}/bg_local_avg"])
+    assert np.where(amb, 0.0, np.abs(gb - g[f"ploss_{tag}/bg_local_avg_grad"])).max() <= 1e-5 * np.abs(g[f"ploss_{tag}/bg_local_avg_grad"]).max()
+    # 'global_avg' ignores the patch
+    cur = torch.from_numpy(cur_np).to(dev).requires_grad_(True)
+    a = losses.compute_background_loss(cur, orig, pc, patch, (64, 64))
+    b = losses.compute_background_loss(cur, orig, pc, 1, (64, 64))
+    assert a.item() == b.item()
+    with pytest.raises(ValueError):
+        losses.compute_foreground_loss(cur, orig, pc, 0, (64, 64))
+
+
+def test_fused_guidance_loss_with_patches(dev, golden_pc):
+    """guidance_loss with fg_patch_size / bg_patch_size > 1 over three layers (two of them resized), fused launch when the
+    patches agree and one launch per term when they differ; the patch kernel with patch 1 equals the patch-1 kernels."""
+    from diffusionhandles_b200 import losses
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
+    _, gp = golden_pc
+    corr = gp["cfg1/corr"].astype(np.int64)
+    pc = GuidedStableDiffuser().process_correspondences(torch.from_numpy(corr), 512, 0)
+    pc_np = O.process_correspondences(corr, 512, 0)
+    shapes = [(24, 32), (12, 64), (10, 16)]
+    gen = torch.Generator().manual_seed(21)
+    curs = [torch.randn((c, s, s), generator=gen) for c, s in shapes]
+    origs = [torch.randn((c, s, s), generator=gen) for c, s in shapes]
+    fgw, bgw = [3.0, 1.5, 0.5], [2.0, 0.25, 1.0]
+    for lt, fp, bp in (("local_avg", 3, 3), ("local_avg", 3, 5), ("global_avg", 5, 5)):
+        dc = [c.to(dev).requires_grad_(True) for c in curs]
+        total, parts = losses.guidance_loss(dc, [o.to(dev) for o in origs], pc, fgw, bgw, bg_loss_type=lt, patch_size=fp, bg_patch_size=bp)
+        grads = torch.autograd.grad(total, dc)
+        ref_total = 0.0
+        for l, (c, o_) in enumerate(zip(curs, origs)):
+            vf, gf = O.foreground_loss(c.numpy(), o_.numpy(), pc_np, patch=fp)
+            vb, gb = O.background_loss(c.numpy(), o_.numpy(), pc_np, loss_type=lt, patch=bp)
+            ref_total += fgw[l] * vf + bgw[l] * vb
+            assert abs(parts[2 * l].item() - vf) <= 1e-5 * abs(vf) and abs(parts[2 * l + 1].item() - vb) <= 1e-5 * abs(vb)
+            ref_g = fgw[l] * gf + bgw[l] * gb
+            amb = O.loss_sign_ambiguity(c.numpy(), o_.numpy(), pc_np, bg_loss_type=lt, patch=fp, bg_patch=bp)
+            assert amb.mean() < 1e-2          # small maps: one ambiguous difference touches a whole patch of a 16x16 plane
+            assert np.where(amb, 0.0, np.abs(grads[l].cpu().numpy() - ref_g)).max() <= 1e-5 * np.abs(ref_g).max()
+        assert abs(total.item() - ref_total) <= 1e-5 * abs(ref_total)
+    # the general kernel at patch 1 against the specialised patch-1 kernels
+    for lt in ("global_avg", "local_avg"):
+        kind = 1 if lt == "global_avg" else 2
+        plan = losses._plan_for(pc, 64, dev)
+        dcur, dorig = [c.to(dev) for c in curs], [o.to(dev) for o in origs]
+        o1, g1 = losses._launch(dcur, dorig, [True] * 3, fgw, bgw, plan, 1, kind, 1)
+        lib = losses.N.load()
+        runner_key = (tuple(tuple(c.shape) for c in dcur), 1, kind, 1)
+        layers, _, _, _ = plan._runners[runner_key]
+        g2 = [torch.empty_like(c) for c in dcur]
+        for i in range(3):
+            layers[i].grad = g2[i].data_ptr()
+        o2 = torch.empty_like(o1)
+        ws = torch.empty(int(lib.dh_guidance_loss_patch_workspace_bytes(3, 24)), dtype=torch.uint8, device=dev)
+        n_fg, n_bo, n_bt, n_bc = plan.n
+        losses.N.check(lib.dh_guidance_loss_patch(layers, 3, 64, 1, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, 1, kind, o2.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream), "patch")
+        assert torch.allclose(o1, o2, rtol=1e-5, atol=0)
+        for a, b in zip(g1, g2):
+            # identical sign counts; only the resize arithmetic may differ in the last bits
+            assert (a - b).abs().max() <= 1e-6 * a.abs().max()
+
+
 def test_fused_guidance_loss_config3(dev, golden_pc):
     """BASELINE config 3 shapes: (1280,32,32), (640,64,64), (320,64,64); weighted sum of 6 terms in one launch,
     against the fp64 oracle, and against stock PyTorch autograd on the GPU running the reference formulas."""
@@ -730,6 +815,13 @@ def test_losses_with_zero_correspondences_are_nan_like_the_reference(dev):
     orig = torch.randn(4, 32, 32, device=dev)
     lf = losses.compute_foreground_loss(cur, orig, pc, 1, (64, 64))
     assert torch.isnan(lf)
+    gf = torch.autograd.grad(lf, cur)[0]
+    assert not gf.any()                    # torch scatters nothing back from an empty gather: gradient 0, not NaN
+    total, _ = losses.guidance_loss([cur], [orig], pc, [1.5], [1.25])
+    gt = torch.autograd.grad(total, cur)[0]
+    assert torch.isnan(total) and torch.isfinite(gt).all() and gt.abs().sum() > 0
+    lf3 = losses.compute_foreground_loss(cur, orig, pc, 3, (64, 64))
+    assert torch.isnan(lf3) and not torch.autograd.grad(lf3, cur)[0].any()
     lb = losses.compute_background_loss(cur, orig, pc, 1, (64, 64))
     assert torch.isfinite(lb)              # the background lists cover the whole grid
     g = torch.autograd.grad(lb, cur)[0]

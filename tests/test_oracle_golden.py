@@ -136,6 +136,31 @@ def test_losses_golden(golden_small, golden_pc, tag):
         O.background_loss(cur, orig, pc, loss_type="nope")
 
 
+@pytest.mark.parametrize("tag", ["p3c4h64", "p5c3h32", "p2c3h16", "p4c2h64"])
+def test_patch_losses_golden(golden_small, golden_pc, tag):
+    """patch_size > 1 (losses.py:62-77), odd and even patches, against values/gradients recorded from the reference."""
+    g = golden_small
+    _, gp = golden_pc
+    pc = O.process_correspondences(gp["cfg1/corr"].astype(np.int64), 512, 0)
+    cur, orig, patch = g[f"ploss_{tag}/cur"], g[f"ploss_{tag}/orig"], int(g[f"ploss_{tag}/patch"])
+    for key, (val, grad) in {"fg": O.foreground_loss(cur, orig, pc, patch=patch),
+                             "bg_local_avg": O.background_loss(cur, orig, pc, loss_type="local_avg", patch=patch)}.items():
+        ref_v, ref_g = g[f"ploss_{tag}/{key}"], g[f"ploss_{tag}/{key}_grad"]
+        assert abs(val - ref_v) <= 1e-5 * abs(ref_v), key
+        amb = O.loss_sign_ambiguity(cur, orig, pc, bg_loss_type="local_avg", patch=patch)
+        assert amb.mean() < 1e-3
+        assert np.where(amb, 0.0, np.abs(grad - ref_g)).max() <= 1e-5 * np.abs(ref_g).max(), key
+
+
+def test_empty_index_lists_give_nan_loss_and_zero_gradient():
+    """torch: the mean over an empty gather is NaN, its backward scatters nothing (verified against the reference)."""
+    cur, orig = np.ones((2, 8, 8), np.float32), np.zeros((2, 8, 8), np.float32)
+    e = np.zeros(0, np.int64)
+    pc = dict(original_x=e, original_y=e, transformed_x=e, transformed_y=e)
+    v, gr = O.foreground_loss(cur, orig, pc)
+    assert np.isnan(v) and not gr.any()
+
+
 def test_guidance_weight_schedule_values():
     s = O.guidance_weight_schedule()
     fg, bg = s(0, 0)
