@@ -841,3 +841,17 @@ def test_api_accepts_cuda_axis_float64_depth_and_noncontiguous(dev, K, golden_pc
     disp, corr = dt.transform_depth(td, tb, tm, K, rot_angle=m["angle"], rot_axis=torch.tensor(m["axis"], device=dev),
                                     translation=torch.tensor(m["translation"], device=dev))
     assert np.array_equal(corr.numpy(), g["cfg1/corr"].astype(np.int64))
+
+
+@pytest.mark.parametrize("axis,angle", [((0.3, 0.9, -0.2), 25.0), ((1.0, 1.0, 0.0), -40.0), ((-2.0, 0.5, 3.0), 70.0)])
+def test_general_rotation_axis_matches_the_oracle(dev, K, axis, angle):
+    """General (non axis-aligned) rotation axes: the reference's np.dot is an sgemv whose rounding depends on its blocking
+    (SURVEY.md A.2), so the contract with the reference is 'isolated pixel differences'; the CUDA path and the oracle use
+    the same fixed order fma(q2,a2, fma(q0,a0, q1*a1)) and must agree bit for bit."""
+    S = 256
+    depth, bg, mask = O.synthetic_scene(S, 17)
+    t = (0.15, -0.05, 0.1)
+    o = O.transform_depth_pc(depth, bg, mask, K_NP, angle, axis, f32_translation(t), poisson=False)
+    eng, res = run_edit(dev, K, depth, bg, mask, angle, axis, t, poisson=False)
+    compare_edit(eng, res, o, S)
+    assert o["correspondences"].shape[0] > 1000
