@@ -188,6 +188,7 @@ struct LossParams {
     int fg_kind;        // 0 = off, 1 = local_avg patch 1
     int bg_kind;        // 0 = off, 1 = global_avg, 2 = local_avg
     float* partial;     // [all channels][2]: fg sum, bg term
+    unsigned int* work_counter;   // zeroed before the launches: channels beyond the first gridDim.x are handed out dynamically
 };
 
 struct LossFinal {
@@ -319,7 +320,13 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid
     const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
     __syncthreads();
 
-    for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x) {
+    // dynamic channel queue: the two kernels of one evaluation overlap (programmatic dependent launch), so CTAs start
+    // at different times; the next channel index is fetched while the current channel is processed
+    __shared__ int s_next;
+    int gc = blockIdx.x;
+    while (gc < p.total_channels) {
+        int nxt = 0;
+        if (tid == 0) nxt = (int)atomicAdd(p.work_counter, 1u) + (int)gridDim.x;
         const int l = layer_of(p, gc);
         const LossLayerDev& L = p.lv[l];
         const int c = gc - L.chan_begin;
@@ -401,7 +408,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid
                 st_cs_f4(g + q, v);
             }
         }
+        if (tid == 0) s_next = nxt;
         __syncthreads();     // cnt / red are reused by the next channel
+        gc = s_next;
     }
     loss_finish(p, fin, red32);
 }
@@ -507,6 +516,8 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __gr
                                                                       const __grid_constant__ ResizeLayout lay) {
     extern __shared__ __align__(16) float rsm[];
     __shared__ __align__(16) ResizeShared sh;
+    // let the flat-layer kernel of the same evaluation (a programmatic dependent launch) start as soon as SM resources free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const int G = kG ? kG : p.G, GG = G * G;
     const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
@@ -549,7 +560,11 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __gr
     }
 
     int cur_layer = -1;
-    for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x) {
+    __shared__ int s_next;
+    int gc = blockIdx.x;
+    while (gc < p.total_channels) {
+        int nxt = 0;
+        if (tid == 0) nxt = (int)atomicAdd(p.work_counter, 1u) + (int)gridDim.x;
         const int l = layer_of(p, gc);
         const LossLayerDev& L = p.lv[l];
         const int c = gc - L.chan_begin;
@@ -663,7 +678,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __gr
                 }
             }
         }
+        if (tid == 0) s_next = nxt;
         __syncthreads();     // planes / cnt / uc / tmp are reused by the next channel
+        gc = s_next;
     }
     loss_finish(p, fin, sh.red32);
 }
@@ -800,6 +817,8 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         q->partial = static_cast<float*>(ws);
     }
     fin.done_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
+    pf.work_counter = fin.done_counter + 1;
+    pr.work_counter = fin.done_counter + 2;
     fin.loss_out = loss_out;
     cudaStream_t st = as_stream(stream);
     int dev = 0, sms = 148;
@@ -843,14 +862,23 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         if (grid_r > pr.total_channels) grid_r = pr.total_channels;
     }
     fin.total_ctas = (unsigned int)(grid_f + grid_r);
-    DH_CUDA_CHECK(cudaMemsetAsync(fin.done_counter, 0, sizeof(unsigned int), st));
+    DH_CUDA_CHECK(cudaMemsetAsync(fin.done_counter, 0, 4 * sizeof(unsigned int), st));
     if (grid_r) {
         resize_kernel<<<grid_r, kLossThreads, smem_r, st>>>(pr, fin, lay);
         DH_LAUNCH_CHECK();
     }
     if (grid_f) {
-        flat_kernel<<<grid_f, kLossThreads, 0, st>>>(pf, fin);
-        DH_LAUNCH_CHECK();
+        // The two kernels are independent (they only meet in loss_finish through an atomic ticket), so the second one is
+        // a programmatic dependent launch: its CTAs become resident as the first kernel's CTAs retire instead of waiting
+        // for the whole grid, which hides the launch gap and the tail of the first kernel.
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid_f); cfg.blockDim = dim3(kLossThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = grid_r ? 1 : 0;
+        DH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flat_kernel, pf, fin));
     }
     return DH_OK;
 }

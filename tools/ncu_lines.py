@@ -21,7 +21,9 @@ for l in dis[start:end]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         off2line[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kfilter = os.environ.get("NCU_KERNEL")          # e.g. regex:loss_flat when the report holds several kernels
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", kfilter] if kfilter else [])
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
