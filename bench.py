@@ -427,9 +427,11 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                          "kernel": "warp_dense_tma_kernel", "ms_per_launch": k3_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WARP * n_edits},
             "cpu_baseline": {"value": cpu_e2e, "unit": UNIT, "cores": cpu_cores, "kind": "port",
-                             "sample": f"{per_worker} edits on each of {cpu_cores} worker processes of the same workload: oracle NumPy "
-                                       f"port of transform_depth_pc + dense maps + torch CPU index gather of the 4-level stack "
-                                       f"(one process alone: {cpu_serial:.1f} warps/s; its gather alone: {cpu_gather:.1f} warps/s)"},
+                             "sample": (f"{per_worker} edits on each of {cpu_cores} worker processes" if per_worker else
+                                        "8 edits in one process (the all-core CPU leg runs at N=1 and in --impl reference)") +
+                                       " of the same workload: oracle NumPy port of transform_depth_pc + dense maps + torch CPU index "
+                                       f"gather of the 4-level stack (one process alone: {cpu_serial:.1f} warps/s; its gather alone: "
+                                       f"{cpu_gather:.1f} warps/s)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_edit() * n_edits,
                     "d2h_bytes_per_step": pipe.d2h_bytes_per_edit() * n_edits, "steps": e2e_steps,
                     "host_numa_binding": host_binding,
