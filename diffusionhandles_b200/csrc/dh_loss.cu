@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
 constexpr int kLossThreads = 256;
 constexpr int kLossWarps = kLossThreads / 32;
 constexpr int kOwnGroups = kMaxG * kMaxG / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
+constexpr int kPairUnroll = 4;   // independent pair chains per thread and iteration in the flat kernel (6 and 8 measured equal)
 constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): 2 * G / h <= 16 for h >= 8
 
 struct LossLayerDev {
@@ -332,51 +333,56 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid
         const int c = gc - L.chan_begin;
         const float* __restrict__ cur = L.cur + (size_t)c * GG;
         const float* __restrict__ org = L.orig + (size_t)c * GG;
-        float4 vc[kOwnGroups], vo[kOwnGroups];
+        // Own cells: four 128-bit groups per thread.  They are consumed right away - background sums, and for the local
+        // background term the sign of (orig - cur) as two bits per cell - so that no plane data stays in registers across
+        // the pair walk (the loads also bring both planes into L1 for the pair gathers).
+        float s1 = 0.0f, s2 = 0.0f;
+        uint32_t sign_pos = 0u, sign_neg = 0u;          // bit 4k+i: orig > cur / orig < cur at own cell i of group k
 #pragma unroll
         for (int k = 0; k < kOwnGroups; ++k) {
             const int q = 4 * (tid + k * kLossThreads);
-            vc[k] = vo[k] = make_float4(0, 0, 0, 0);
             if (q < GG) {
-                vc[k] = __ldg(reinterpret_cast<const float4*>(cur + q));
-                vo[k] = __ldg(reinterpret_cast<const float4*>(org + q));
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cur + q));
+                const float4 o4 = __ldg(reinterpret_cast<const float4*>(org + q));
                 *reinterpret_cast<int4*>(cnt + q) = make_int4(0, 0, 0, 0);
+                const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+                if (p.bg_kind == 1) {
+                    // same association as before: s = fma(w0, v0, fma(w1, v1, fma(w2, v2, fma(w3, v3, s))))
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        s1 = fmaf(wgt(mo, k, i, 0), ov[i], s1);
+                        s2 = fmaf(wgt(mt, k, i, 1), cv[i], s2);
+                    }
+                } else if (p.bg_kind == 2) {
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        const float d = ov[i] - cv[i];
+                        s1 = fmaf(wgt(mc, k, i, 2), fabsf(d), s1);
+                        sign_pos |= (d > 0.0f ? 1u : 0u) << (4 * k + i);
+                        sign_neg |= (d < 0.0f ? 1u : 0u) << (4 * k + i);
+                    }
+                }
             }
         }
         __syncthreads();
-        float acc_f = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        float acc_f = 0.0f;
         if (p.fg_kind) {
-            // four independent pair chains per thread and iteration (memory-level parallelism for the L1 gathers)
-            for (int j0 = tid; j0 < n_pairs; j0 += 4 * kLossThreads) {
-                uint2 e[4];
-                float df[4];
+            // kPairUnroll independent pair chains per thread and iteration (memory-level parallelism for the L1 gathers)
+            for (int j0 = tid; j0 < n_pairs; j0 += kPairUnroll * kLossThreads) {
+                uint2 e[kPairUnroll];
+                float df[kPairUnroll];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kPairUnroll; ++u) {
                     const int j = j0 + u * kLossThreads;
                     e[u] = j < n_pairs ? pairs[j] : make_uint2(0u, 0u);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) df[u] = __ldg(org + (e[u].x & 0xFFFFu)) - __ldg(cur + (e[u].x >> 16));
+                for (int u = 0; u < kPairUnroll; ++u) df[u] = __ldg(org + (e[u].x & 0xFFFFu)) - __ldg(cur + (e[u].x >> 16));
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kPairUnroll; ++u) {
                     acc_f = fmaf((float)e[u].y, fabsf(df[u]), acc_f);
                     if (df[u] != 0.0f && e[u].y) atomicAdd(cnt + (e[u].x >> 16), df[u] > 0.0f ? -(int)e[u].y : (int)e[u].y);
                 }
-            }
-        }
-        if (p.bg_kind == 1) {
-#pragma unroll
-            for (int k = 0; k < kOwnGroups; ++k) {
-                if (4 * (tid + k * kLossThreads) >= GG) break;
-                s1 = fmaf(wgt(mo, k, 0, 0), vo[k].x, fmaf(wgt(mo, k, 1, 0), vo[k].y, fmaf(wgt(mo, k, 2, 0), vo[k].z, fmaf(wgt(mo, k, 3, 0), vo[k].w, s1))));
-                s2 = fmaf(wgt(mt, k, 0, 1), vc[k].x, fmaf(wgt(mt, k, 1, 1), vc[k].y, fmaf(wgt(mt, k, 2, 1), vc[k].z, fmaf(wgt(mt, k, 3, 1), vc[k].w, s2))));
-            }
-        } else if (p.bg_kind == 2) {
-#pragma unroll
-            for (int k = 0; k < kOwnGroups; ++k) {
-                if (4 * (tid + k * kLossThreads) >= GG) break;
-                s1 = fmaf(wgt(mc, k, 0, 2), fabsf(vo[k].x - vc[k].x), fmaf(wgt(mc, k, 1, 2), fabsf(vo[k].y - vc[k].y),
-                     fmaf(wgt(mc, k, 2, 2), fabsf(vo[k].z - vc[k].z), fmaf(wgt(mc, k, 3, 2), fabsf(vo[k].w - vc[k].w), s1))));
             }
         }
         block_sum3(acc_f, s1, s2, red);       // (its barrier also orders the cnt atomics)
@@ -397,15 +403,18 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid
                 const int q = 4 * (tid + k * kLossThreads);
                 if (q >= GG) break;
                 const int4 ci = *reinterpret_cast<const int4*>(cnt + q);
-                float4 v = make_float4((float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale);
+                float v[4] = {(float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale};
                 if (p.bg_kind == 1) {
-                    v.x = fmaf(wgt(mt, k, 0, 1), bscale, v.x); v.y = fmaf(wgt(mt, k, 1, 1), bscale, v.y);
-                    v.z = fmaf(wgt(mt, k, 2, 1), bscale, v.z); v.w = fmaf(wgt(mt, k, 3, 1), bscale, v.w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = fmaf(wgt(mt, k, i, 1), bscale, v[i]);
                 } else if (p.bg_kind == 2) {
-                    v.x -= sgn(vo[k].x - vc[k].x) * wgt(mc, k, 0, 2) * lscale; v.y -= sgn(vo[k].y - vc[k].y) * wgt(mc, k, 1, 2) * lscale;
-                    v.z -= sgn(vo[k].z - vc[k].z) * wgt(mc, k, 2, 2) * lscale; v.w -= sgn(vo[k].w - vc[k].w) * wgt(mc, k, 3, 2) * lscale;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float sg = (float)((sign_pos >> (4 * k + i)) & 1u) - (float)((sign_neg >> (4 * k + i)) & 1u);
+                        v[i] -= sg * wgt(mc, k, i, 2) * lscale;
+                    }
                 }
-                st_cs_f4(g + q, v);
+                st_cs_f4(g + q, make_float4(v[0], v[1], v[2], v[3]));
             }
         }
         if (tid == 0) s_next = nxt;
