@@ -77,6 +77,7 @@ _SIGNATURES = {
     "dh_process_correspondences": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "dh_dense_source_map": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dh_dense_source_maps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, C.POINTER(c_int), c_int, c_void_p, c_void_p]),
     "dh_warp_gather_list": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dh_warp_gather_dense": (c_int, [C.POINTER(dh_warp_level), c_int, c_int, c_void_p]),
     "dh_guidance_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dh_scale_inplace_many": (c_int, [C.POINTER(c_void_p), C.POINTER(c_size_t), c_int, c_void_p, c_void_p]),
     "dh_raster_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dh_rasterize_meshes": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_float,
                                     c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -174,7 +176,14 @@ def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None, name: st
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_handle(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (the raw getter avoids building a Stream object per call)."""
+    if _raw_stream is not None:
+        idx = device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -707,6 +707,32 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
     if (i < (n & 3)) data[n4 * 4 + i] *= s;
 }
 
+struct ScaleMany {
+    float* data[kMaxLossLayers];
+    unsigned long long n[kMaxLossLayers];
+    unsigned int block_begin[kMaxLossLayers + 1];
+    int count;
+};
+
+// several tensors in one launch (autograd's backward of the fused multi-layer loss)
+__global__ void __launch_bounds__(256) scale_many_kernel(const __grid_constant__ ScaleMany m, const float* __restrict__ scale) {
+    const float s = *scale;
+    if (s == 1.0f) return;
+    int t = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLossLayers; ++i)
+        if (i < m.count && blockIdx.x >= m.block_begin[i]) t = i;
+    float* data = m.data[t];
+    const size_t n = m.n[t], n4 = n / 4;
+    const size_t i = (size_t)(blockIdx.x - m.block_begin[t]) * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 v = reinterpret_cast<float4*>(data)[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4*>(data)[i] = v;
+    }
+    if (i < (n & 3)) data[n4 * 4 + i] *= s;
+}
+
 }  // namespace dh
 
 using namespace dh;
@@ -830,9 +856,22 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     pr.work_counter = fin.done_counter + 2;
     fin.loss_out = loss_out;
     cudaStream_t st = as_stream(stream);
-    int dev = 0, sms = 148;
+    // per-process caches of the launch geometry queries (this entry point runs every denoising step)
+    struct LaunchCache {
+        int sms, occ_flat[2], occ_resize[2];
+        size_t occ_resize_smem[2], smem_attr_set[2];
+    };
+    static LaunchCache caches[64];          // zero-initialised; one entry per device (function attributes are per device)
+    int dev = 0;
     DH_CUDA_CHECK(cudaGetDevice(&dev));
-    DH_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 0 || dev >= 64) return DH_ERR_UNSUPPORTED;
+    LaunchCache& lc = caches[dev];
+    if (!lc.sms) DH_CUDA_CHECK(cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = lc.sms;
+    int (&occ_flat)[2] = lc.occ_flat;
+    int (&occ_resize)[2] = lc.occ_resize;
+    size_t (&occ_resize_smem)[2] = lc.occ_resize_smem;
+    size_t (&smem_attr_set)[2] = lc.smem_attr_set;
     // grids: persistent CTAs, as many as fit per SM
     int grid_f = 0, grid_r = 0;
     ResizeLayout lay;
@@ -841,9 +880,12 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
     auto flat_kernel = (plan_flags & 1) ? loss_flat_kernel<true> : loss_flat_kernel<false>;
     if (pf.total_channels) {
-        int per_sm = 1;
-        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_kernel, kLossThreads, 0));
-        grid_f = sms * (per_sm < 1 ? 1 : per_sm);
+        int& per_sm = occ_flat[(plan_flags & 1) ? 1 : 0];
+        if (!per_sm) {
+            DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_kernel, kLossThreads, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        grid_f = sms * per_sm;
         if (grid_f > pf.total_channels) grid_f = pf.total_channels;
     }
     auto resize_kernel = grid == 64 ? loss_resize_kernel<64> : loss_resize_kernel<0>;
@@ -864,10 +906,18 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         lay.total = o;
         lay.box_cap = cap;
         smem_r = sizeof(float) * (size_t)o;
-        DH_CUDA_CHECK(cudaFuncSetAttribute(resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-        int per_sm = 1;
-        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resize_kernel, kLossThreads, smem_r));
-        grid_r = sms * (per_sm < 1 ? 1 : per_sm);
+        const int rk = grid == 64 ? 1 : 0;
+        if (smem_r > smem_attr_set[rk]) {
+            DH_CUDA_CHECK(cudaFuncSetAttribute(resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            smem_attr_set[rk] = smem_r;
+        }
+        if (!occ_resize[rk] || occ_resize_smem[rk] != smem_r) {
+            int per_sm = 1;
+            DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resize_kernel, kLossThreads, smem_r));
+            occ_resize[rk] = per_sm < 1 ? 1 : per_sm;
+            occ_resize_smem[rk] = smem_r;
+        }
+        grid_r = sms * occ_resize[rk];
         if (grid_r > pr.total_channels) grid_r = pr.total_channels;
     }
     fin.total_ctas = (unsigned int)(grid_f + grid_r);
@@ -898,6 +948,26 @@ int dh_scale_inplace(float* data, size_t n, const float* scale, void* stream) {
     if (reinterpret_cast<uintptr_t>(data) & 15) return DH_ERR_INVALID_ARGUMENT;
     const size_t threads = n / 4 > 3 ? n / 4 : 4;
     scale_inplace_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(data, n, scale);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
+int dh_scale_inplace_many(float* const* data_host, const size_t* n_host, int count, const float* scale, void* stream) {
+    DH_REQUIRE(data_host && n_host && scale && count >= 0 && count <= kMaxLossLayers);
+    ScaleMany m;
+    memset(&m, 0, sizeof(m));
+    unsigned int blocks = 0;
+    for (int i = 0; i < count; ++i) {
+        if (!data_host[i] || n_host[i] == 0) continue;
+        if (reinterpret_cast<uintptr_t>(data_host[i]) & 15) return DH_ERR_INVALID_ARGUMENT;
+        const size_t threads = n_host[i] / 4 > 3 ? n_host[i] / 4 : 4;
+        m.data[m.count] = data_host[i]; m.n[m.count] = n_host[i]; m.block_begin[m.count] = blocks;
+        blocks += (unsigned int)((threads + 255) / 256);
+        ++m.count;
+    }
+    if (m.count == 0) return DH_OK;
+    m.block_begin[m.count] = blocks;
+    scale_many_kernel<<<blocks, 256, 0, as_stream(stream)>>>(m, scale);
     DH_LAUNCH_CHECK();
     return DH_OK;
 }

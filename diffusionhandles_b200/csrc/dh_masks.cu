@@ -271,6 +271,68 @@ __global__ void __launch_bounds__(256) dense_map_finalize_kernel(const int64_t* 
     if (lane_id() == 0) *m = res;
 }
 
+// ---- all levels of a stack in one pass --------------------------------------------------------------
+constexpr int kMaxMapLevels = 8;
+struct MapLevels {
+    int n_levels, img_res;
+    int side[kMaxMapLevels];
+    int cell_begin[kMaxMapLevels + 1];      // prefix sums of side^2
+    size_t map_begin[kMaxMapLevels];        // offset (ints) of level l inside the map buffer: B * cell_begin[l]
+};
+
+__global__ void __launch_bounds__(256) dense_maps_scatter_kernel(const int64_t* __restrict__ corr, const int32_t* __restrict__ n_corr,
+                                                                 int corr_stride_rows, const __grid_constant__ MapLevels lv,
+                                                                 int32_t* __restrict__ maps) {
+    const int e = blockIdx.y;
+    const int n_e = n_corr[e];
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_e; n += gridDim.x * blockDim.x) {
+        const longlong4 v = *reinterpret_cast<const longlong4*>(corr + ((size_t)e * corr_stride_rows + n) * 4);
+#pragma unroll
+        for (int l = 0; l < kMaxMapLevels; ++l) {
+            if (l >= lv.n_levels) break;
+            const int side = lv.side[l], r = lv.img_res / side;
+            const int d = (int)(v.w / r) * side + (int)(v.z / r);
+            atomicMin(maps + lv.map_begin[l] + (size_t)e * side * side + d, n);
+        }
+    }
+}
+
+// one warp per (level, destination cell)
+__global__ void __launch_bounds__(256) dense_maps_finalize_kernel(const int64_t* __restrict__ corr, int corr_stride_rows,
+                                                                  const int32_t* __restrict__ winner_src,
+                                                                  const __grid_constant__ MapLevels lv, int32_t* __restrict__ maps) {
+    const int e = blockIdx.y;
+    const int gcell = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (gcell >= lv.cell_begin[lv.n_levels]) return;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxMapLevels; ++i)
+        if (i < lv.n_levels && gcell >= lv.cell_begin[i]) l = i;
+    const int side = lv.side[l], img_res = lv.img_res, r = img_res / side, cell = gcell - lv.cell_begin[l];
+    int32_t* m = maps + lv.map_begin[l] + (size_t)e * side * side + cell;
+    const int first = *m;
+    int res = -1;
+    if (first < 0x7F000000) {
+        const longlong4 v = *reinterpret_cast<const longlong4*>(corr + ((size_t)e * corr_stride_rows + first) * 4);
+        res = (int)(v.y / r) * side + (int)(v.x / r);
+    } else if (winner_src) {
+        const int cy = cell / side, cx = cell - cy * side;
+        const int32_t* ws = winner_src + (size_t)e * img_res * img_res;
+        const int n = r * r;
+        for (int k0 = 0; k0 < n && res < 0; k0 += 32) {
+            const int k = k0 + lane_id();
+            int s_ = -1;
+            if (k < n) s_ = ws[(cy * r + k / r) * img_res + cx * r + k % r];
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, s_ >= 0);
+            if (b) {
+                s_ = __shfl_sync(0xFFFFFFFFu, s_, __ffs(b) - 1);
+                res = ((s_ / img_res) / r) * side + (s_ % img_res) / r;
+            }
+        }
+    }
+    if (lane_id() == 0) *m = res;
+}
+
 }  // namespace dh
 
 using namespace dh;
@@ -370,6 +432,32 @@ int dh_dense_source_map(const int64_t* corr, const int32_t* n_corr, int corr_str
     DH_LAUNCH_CHECK();
     dim3 g2((side * side + 7) / 8, B);
     dense_map_finalize_kernel<<<g2, 256, 0, st>>>(corr, corr_stride_rows, winner_src, img_res, side, src_map);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
+int dh_dense_source_maps(const int64_t* corr, const int32_t* n_corr, int corr_stride_rows, const int32_t* winner_src, int B,
+                         int img_res, const int* sides_host, int n_levels, int32_t* maps, void* stream) {
+    DH_REQUIRE(corr && n_corr && maps && sides_host && B >= 1 && n_levels >= 1 && n_levels <= kMaxMapLevels);
+    DH_REQUIRE(corr_stride_rows >= 1);
+    MapLevels lv;
+    memset(&lv, 0, sizeof(lv));
+    lv.n_levels = n_levels; lv.img_res = img_res;
+    int cells = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const int side = sides_host[l];
+        DH_REQUIRE(side >= 1 && img_res >= side && img_res % side == 0);
+        lv.side[l] = side; lv.cell_begin[l] = cells; lv.map_begin[l] = (size_t)B * cells;
+        cells += side * side;
+    }
+    lv.cell_begin[n_levels] = cells;
+    cudaStream_t st = as_stream(stream);
+    DH_CUDA_CHECK(cudaMemsetAsync(maps, 0x7F, sizeof(int32_t) * (size_t)B * cells, st));
+    int gx = (corr_stride_rows + 255) / 256;
+    if (gx > 64) gx = 64;                         // grid-stride: the capacity is P rows, the lists are ~10x shorter
+    dense_maps_scatter_kernel<<<dim3(gx, B), 256, 0, st>>>(corr, n_corr, corr_stride_rows, lv, maps);
+    DH_LAUNCH_CHECK();
+    dense_maps_finalize_kernel<<<dim3((cells + 7) / 8, B), 256, 0, st>>>(corr, corr_stride_rows, winner_src, lv, maps);
     DH_LAUNCH_CHECK();
     return DH_OK;
 }

@@ -147,7 +147,7 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         layers[i].fg_weight, layers[i].bg_weight = float(fgw[i]), float(bgw[i])
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
     n_fg, n_bo, n_bt, n_bc = plan.n
-    st = torch.cuda.current_stream(dev).cuda_stream
+    st = N.stream_handle(dev)
     if patch == 1:
         N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
                                      fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
@@ -167,7 +167,7 @@ class _FusedLoss(torch.autograd.Function):
                              spec.get("patch", 1))
         ctx.grads = grads
         ctx.n_inputs = len(acts)
-        total, parts = out[0].clone(), out[1:].clone()
+        total, parts = out[0], out[1:]          # views of a buffer that is private to this call
         ctx.mark_non_differentiable(parts)
         return total, parts
 
@@ -175,16 +175,17 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, g_total, _g_parts):
         lib = N.load()
         res = [None] * (1 + ctx.n_inputs)
-        scale, st = None, None
-        for i, g in enumerate(ctx.grads):
-            if g is None:
-                continue
-            if scale is None:
-                scale = _as_f32(g_total, g.device).reshape(1)
-                st = torch.cuda.current_stream(g.device).cuda_stream
-            N.check(lib.dh_scale_inplace(g.data_ptr(), g.numel(), scale.data_ptr(), st), "dh_scale_inplace")
-            res[1 + i] = g
+        live = [(i, g) for i, g in enumerate(ctx.grads) if g is not None]
         ctx.grads = None
+        if live:
+            dev = live[0][1].device
+            scale = _as_f32(g_total, dev).reshape(1)
+            ptrs = (C.c_void_p * len(live))(*[g.data_ptr() for _, g in live])
+            sizes = (C.c_size_t * len(live))(*[g.numel() for _, g in live])
+            # one launch for every layer; exits on the device when the incoming gradient is 1
+            N.check(lib.dh_scale_inplace_many(ptrs, sizes, len(live), scale.data_ptr(), N.stream_handle(dev)), "dh_scale_inplace_many")
+            for i, g in live:
+                res[1 + i] = g
         return tuple(res)
 
 

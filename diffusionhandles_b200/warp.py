@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import ctypes as C
+
 import torch
 
 from . import _native as N
@@ -43,14 +45,19 @@ def dense_source_maps(corr: torch.Tensor, n_corr: torch.Tensor, img_res: int, si
     lib = N.load()
     dev = corr.device
     B, cap = corr.shape[0], corr.shape[1]
-    st = N.stream_handle(dev)
-    maps = []
-    for side in sides:
-        m = torch.empty((B, side * side), dtype=torch.int32, device=dev)
-        N.check(lib.dh_dense_source_map(N.ptr(corr, torch.int64, "corr"), N.ptr(n_corr, torch.int32, "n_corr"), cap,
-                                        N.ptr(winner_src, torch.int32, "winner_src") if winner_src is not None else None,
-                                        B, img_res, side, N.ptr(m), st), "dh_dense_source_map")
-        maps.append(m)
+    sides = [int(v) for v in sides]
+    if not 1 <= len(sides) <= 8:
+        raise ValueError("between 1 and 8 levels are supported")
+    # one buffer, level-major; one scatter + one finalize launch for the whole stack
+    buf = torch.empty(B * sum(v * v for v in sides), dtype=torch.int32, device=dev)
+    arr = (C.c_int * len(sides))(*sides)
+    N.check(lib.dh_dense_source_maps(N.ptr(corr, torch.int64, "corr"), N.ptr(n_corr, torch.int32, "n_corr"), cap,
+                                     N.ptr(winner_src, torch.int32, "winner_src") if winner_src is not None else None,
+                                     B, img_res, arr, len(sides), N.ptr(buf), N.stream_handle(dev)), "dh_dense_source_maps")
+    maps, o = [], 0
+    for v in sides:
+        maps.append(buf[o:o + B * v * v].view(B, v * v))
+        o += B * v * v
     return maps
 
 

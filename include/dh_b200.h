@@ -183,6 +183,11 @@ int dh_process_correspondences(const int64_t* corr, int n_corr, int img_res, int
  * a splat winner; else -1.  side = cells per image side at this level. */
 int dh_dense_source_map(const int64_t* corr, const int32_t* n_corr, int corr_stride_rows, const int32_t* winner_src,
                         int B, int img_res, int side, int32_t* src_map, void* stream);
+/* All levels of a stack in one pass (the correspondences are read once): sides_host[l] = cells per side of level l
+ * (HOST array); maps = one buffer of B * sum(side_l^2) ints, level-major (level l starts at B * sum_{k<l} side_k^2,
+ * inside it edit-major like src_map above). */
+int dh_dense_source_maps(const int64_t* corr, const int32_t* n_corr, int corr_stride_rows, const int32_t* winner_src,
+                         int B, int img_res, const int* sides_host, int n_levels, int32_t* maps, void* stream);
 
 /* ---- K3, row 9: the activation warp ----------------------------------------------------------------
  * list form : out[c][n] = in[c][idx[n]]            (losses.py:46-47, :80)
@@ -243,6 +248,8 @@ int dh_guidance_loss_patch(const dh_loss_layer* layers_host, int n_layers, int g
                            float* loss_out, void* ws, size_t ws_bytes, void* stream);
 /* grads *= *scale (device scalar); exits early on the device when *scale == 1. */
 int dh_scale_inplace(float* data, size_t n, const float* scale, void* stream);
+/* The same for up to 8 tensors in one launch (HOST arrays of device pointers and element counts). */
+int dh_scale_inplace_many(float* const* data_host, const size_t* n_host, int count, const float* scale, void* stream);
 
 /* ---- 8(f) rank 1: Poisson hole fill of the edited disparity, depth_transform.py:346-363, :535-587 ----
  * Unknown pixels = mask_a XOR mask_b (cleaned ^ raw target mask; mask_b may be NULL).  Solves the masked
