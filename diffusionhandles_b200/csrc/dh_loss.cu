@@ -6,19 +6,19 @@
 // (1) dh_build_loss_plan - once per edit.  The correspondence list has ~6x duplicates at the 64x64 loss grid
 //     (SURVEY.md "hard parts"); the plan groups it by DESTINATION cell (counting sort) and collapses equal
 //     (src, dst) cell pairs into one entry with a multiplicity, giving a CSR over destination cells
-//     (row_ptr, pairs = src | mult << 16) plus per-cell multiplicities of the three background lists.
+//     (row_ptr, 8-byte pairs: src | dst << 16, multiplicity) plus per-cell multiplicities of the three background lists.
 //
-// (2) dh_guidance_loss - every denoising step.  One persistent CTA per SM walks over (layer, channel)
-//     planes: the current and the recorded plane are staged in shared memory with TMA bulk copies
-//     (double buffered, mbarrier complete_tx), optionally resized bilinearly to the loss grid, then every
-//     thread owns a fixed, interleaved set of destination cells and evaluates
+// (2) dh_guidance_loss - every denoising step.  Two kernels of small persistent CTAs (256 threads, three per SM) pull
+//     (layer, channel) planes from a dynamic queue and evaluate, per plane,
 //         L_fg  = 1/(C N)  sum_pairs mult * |up(orig)[src] - up(cur)[dst]|
-//         dL/dup(cur)[dst] = -1/(C N) sum_pairs mult * sign(...)          (INTEGER accumulation per cell)
-//     and the background term, without any atomic: the gradient is gathered per destination cell, so it is
-//     bit-reproducible (the reference's index_put(accumulate=True) backward is not, on CUDA).  The gradient is
-//     written at native resolution (transposed bilinear resize in gather form).  Loss value and gradient come
-//     out of the same pass: algorithmic traffic = read cur + read orig + write grad.
-//     A tiny second kernel reduces the per-channel partial sums in a fixed order.
+//         dL/dup(cur)[dst] = -1/(C N) sum_pairs mult * sign(...)
+//     plus the background term.  The sign terms are accumulated as INTEGERS per destination cell (shared-memory
+//     atomics): integer addition is associative, so the gradient is bit-reproducible (the reference's
+//     index_put(accumulate=True) backward is not, on CUDA).  Layers smaller than the loss grid are resized
+//     bilinearly inside the box of pair cells only, and their gradient is written at native resolution through
+//     the transposed resize in gather form.  Loss value and gradient come out of the same pass: algorithmic
+//     traffic = read cur + read orig + write grad.  The last CTA to finish reduces the per-channel partial sums in
+//     a fixed order; the second kernel is a programmatic dependent launch so that it fills the SMs as the first drains.
 #include "dh_common.cuh"
 #include "dh_loss_plan.cuh"
 
