@@ -139,8 +139,34 @@ def config4():
         del eng
 
 
+def config2_recorded_stack():
+    """SURVEY.md 8(d) config 2, recorded-stack variant: the three recorded levels (1280,32^2), (640,64^2), (320,64^2) for
+    all T = 50 timesteps of one edit warped through that edit's maps: 1.05 GB read + 1.05 GB written."""
+    K = GuidedStableDiffuser.get_depth_intrinsics()
+    depth, bg, mask = synthetic_scene(512, 0)
+    eng = EditEngine(dev, 1, 512, 512)
+    res = eng.run(*(torch.from_numpy(a).to(dev)[None].contiguous() for a in (depth, bg, mask)), K,
+                  [make_rigid(30.0, [0.0, 1.0, 0.0], [0.3, 0.0, 0.2])], poisson=False)
+    shapes = [(1280, 32), (640, 64), (320, 64)]
+    T = 50
+    maps1 = warp.dense_source_maps(res.corr, res.n_corr, 512, [s for _, s in shapes], res.winner_src)
+    maps = [m.expand(T, -1).contiguous() for m in maps1]             # the same edit at every timestep
+    g = torch.Generator(device=dev).manual_seed(5)
+    stacks = [torch.randn((T, c, s, s), generator=g, device=dev) for c, s in shapes]
+    outs = [torch.empty_like(a) for a in stacks]
+    med, mn = timeit(lambda: warp.warp_stacks(stacks, maps, outs), n=20, warm=3)
+    for a, m, o in zip(stacks, maps, outs):
+        idx = m[7].long().clamp(min=0)
+        assert torch.equal(o[7].flatten(1), a[7].flatten(1)[:, idx] * (m[7] >= 0))
+    algo = 2 * sum(a.numel() for a in stacks) * 4 + sum(m.numel() for m in maps) * 4
+    print(json.dumps({"config": "config2_recorded_stack", "timesteps": T, "ms_per_edit": med, "algorithmic_bytes": algo,
+                      "achieved_gbs": algo / med / 1e6, "frac_of_hbm_peak": algo / med / 1e6 / PEAK}), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["1", "3", "4"]
+    which = sys.argv[1:] or ["1", "2", "3", "4"]
+    if "2" in which:
+        config2_recorded_stack()
     if "1" in which:
         config1_and_5()
     if "3" in which:
