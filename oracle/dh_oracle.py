@@ -736,9 +736,41 @@ def guidance_weight_schedule(fg_weight: float = 1.5, bg_weight: float = 1.25, gu
 # --------------------------------------------------------------------------------------------
 # synthetic workloads of SURVEY.md 8(d)
 # --------------------------------------------------------------------------------------------
+def smooth_scene(S: int = 512, seed: int = 0):
+    """A scene closer to the reference's fixtures than the config-1 recipe: smooth curved surfaces (no per-pixel noise, so
+    neighbouring points project to neighbouring pixels and z-fights come from geometry), an irregular foreground made of
+    overlapping ellipses with a hole, a thin bar and a detached blob.  Plain arithmetic on seeded NumPy draws, rounded to
+    fp32 once, so every box regenerates the same arrays."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float64) / S
+    bg = 3.6 + 1.1 * yy + 0.25 * (xx - 0.5) ** 2 + 0.08 * yy * xx
+    mask = np.zeros((S, S), bool)
+    fg = np.full((S, S), 10.0)
+    for _ in range(3):
+        cx, cy = rng.uniform(0.35, 0.65), rng.uniform(0.4, 0.7)
+        ax, ay = rng.uniform(0.08, 0.2), rng.uniform(0.08, 0.2)
+        r2 = ((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2
+        inside = r2 < 1.0
+        bump = 2.4 + 0.3 * (cy - 0.5) - 0.35 * np.sqrt(np.maximum(0.0, 1.0 - r2)) + 0.15 * (xx - cx)
+        fg = np.where(inside, np.minimum(fg, bump), fg)
+        mask |= inside
+    hx, hy = rng.uniform(0.45, 0.55), rng.uniform(0.5, 0.6)
+    mask &= ~(((xx - hx) / 0.03) ** 2 + ((yy - hy) / 0.04) ** 2 < 1.0)            # a hole
+    bar = (np.abs(yy - 0.3) < 1.5 / S) & (xx > 0.2) & (xx < 0.8)                   # a 3-pixel bar
+    blob = ((xx - 0.15) / 0.04) ** 2 + ((yy - 0.8) / 0.05) ** 2 < 1.0               # a detached blob
+    fg = np.where(bar & ~mask, 2.0 + 0.2 * xx, fg)
+    fg = np.where(blob & ~mask, 2.8 - 0.2 * yy, fg)
+    mask |= bar | blob
+    depth = np.where(mask, fg, bg)
+    return depth.astype(f32), bg.astype(f32), mask.astype(f32)
+
+
 def synthetic_scene(S: int = 512, seed: int = 0, cx: Optional[float] = None, cy: Optional[float] = None,
-                    radius: Optional[float] = None, quantize: Optional[float] = None):
-    """Config-1 recipe (scaled with S): bg_depth = 4 + row/S + 0.05*rand, fg = 2 + 0.3*rand inside a disc."""
+                    radius: Optional[float] = None, quantize: Optional[float] = None, kind: str = "disc"):
+    """Config-1 recipe (scaled with S): bg_depth = 4 + row/S + 0.05*rand, fg = 2 + 0.3*rand inside a disc;
+    ``kind='smooth'`` gives ``smooth_scene``."""
+    if kind == "smooth":
+        return smooth_scene(S, seed)
     import torch
     g = torch.Generator().manual_seed(seed)
     rows = torch.arange(S, dtype=torch.float32)[:, None]

@@ -34,6 +34,9 @@ PC_CASES = {
     "cfg1_norm": (dict(S=512, seed=0), 30.0, (0.0, 1.0, 0.0), (0.3, 0.0, 0.2), True),
     "zaxis_all_offscreen": (dict(S=512, seed=6, radius=60.0), 60.0, (0.0, 0.0, 1.0), (-4.0, 0.0, -1.5), False),
     "axis_scaled": (dict(S=512, seed=7, radius=80.0), -35.0, (0.0, 2.5, 0.0), (0.1, 0.05, -0.3), False),
+    # smooth surfaces, irregular mask with a hole, a thin bar and a detached blob (closer to the reference's fixtures)
+    "smooth25":  (dict(S=512, seed=21, kind="smooth"), 25.0, (0.0, 1.0, 0.0), (0.25, 0.0, 0.1), False),
+    "smooth_m50": (dict(S=512, seed=22, kind="smooth"), -50.0, (0.0, 1.0, 0.0), (-0.4, 0.05, 0.3), True),
 }
 
 

@@ -71,7 +71,7 @@ def compare_edit(eng, res, o, S, check_points=True):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "neg60", "occl90", "zties45", "xaxis20", "identity", "cfg1_norm",
-                                  "zaxis_all_offscreen", "axis_scaled"])
+                                  "zaxis_all_offscreen", "axis_scaled", "smooth25", "smooth_m50"])
 def test_pc_edit_vs_oracle_and_golden(dev, K, golden_pc, name):
     meta, g = golden_pc
     m = meta[name]

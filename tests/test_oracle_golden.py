@@ -23,7 +23,7 @@ def test_linspace_matches_torch_cpu():
 
 
 @pytest.mark.parametrize("name", ["cfg1", "neg60", "occl90", "zties45", "xaxis20", "identity", "cfg1_norm",
-                                  "zaxis_all_offscreen", "axis_scaled"])
+                                  "zaxis_all_offscreen", "axis_scaled", "smooth25", "smooth_m50"])
 def test_pc_transform_against_reference_golden(golden_pc, name):
     meta, g = golden_pc
     m = meta[name]
