@@ -18,49 +18,45 @@ from .utils import pack_correspondences
 
 
 def normalize_depth(depth, bounds=None, return_bounds=False):
-    """depth_transform.py:15-28 - 255*(x-min)/(max-min) per batch element (elementwise torch ops, any device)."""
+    """depth_transform.py:15-28: maps each batch element linearly onto [0, 255]; ``bounds`` = (min, max) tensors reuse another
+    image's range (use_input_depth_normalization).  Elementwise torch ops in the reference's operation order
+    (255 * (x - min), then the division), on whatever device ``depth`` lives."""
     if depth.dim() != 4:
-        raise RuntimeError(f'Expected depth to have 4 dimensions, got {depth.dim()}')
-    if bounds is None:
-        max_depth = depth.view(depth.shape[0], -1).max(dim=-1).values[..., None, None, None]
-        min_depth = depth.view(depth.shape[0], -1).min(dim=-1).values[..., None, None, None]
+        raise RuntimeError(f"normalize_depth expects a (B,1,H,W) tensor, got {depth.dim()} dimensions")
+    if bounds is not None:
+        lo, hi = bounds
     else:
-        min_depth, max_depth = bounds
-    if return_bounds:
-        return 255 * (depth - min_depth) / (max_depth - min_depth), (min_depth, max_depth)
-    return 255 * (depth - min_depth) / (max_depth - min_depth)
+        lo, hi = torch.aminmax(depth.flatten(start_dim=1), dim=1)
+        lo, hi = lo.reshape(-1, 1, 1, 1), hi.reshape(-1, 1, 1, 1)
+    scaled = (depth - lo) * 255 / (hi - lo)
+    return (scaled, (lo, hi)) if return_bounds else scaled
 
 
 def depth_to_mesh(depth: torch.Tensor, intrinsics: torch.Tensor, extrinsics_R: torch.Tensor = None,
                   extrinsics_t: torch.Tensor = None, mask: torch.Tensor = None):
-    """depth_transform.py:30-71 - triangulate a depth map: one vertex per (masked) pixel (unprojected on the device),
-    two counter-clockwise triangles per 2x2 pixel block whose corners are all inside the mask, and a per-vertex
-    ``color`` attribute (x/(W-1), y/(H-1), mask flag) that the renderer carries to the target image."""
+    """depth_transform.py:30-71: a depth map as a triangle mesh.  One vertex per pixel inside ``mask`` (all pixels without
+    one), unprojected on the device; every 2x2 block of pixels whose corners are all vertices gives two counter-clockwise
+    triangles (bottom-left, top-right, top-left) and (bottom-left, bottom-right, top-right), blocks in raster order; the
+    per-vertex ``color`` attribute is (x/(W-1), y/(H-1), 1 if a mask was given else 0), which the renderer carries to the
+    target image as the source coordinate of each rendered pixel."""
     from .mesh import Mesh
-    if mask is not None:
-        mask = mask.view(mask.shape[-2], mask.shape[-1])
     H, W = depth.shape[-2], depth.shape[-1]
-    verts = depth_to_world_coords(depth, intrinsics=intrinsics, extrinsics_R=extrinsics_R, extrinsics_t=extrinsics_t)
-    if mask is not None:
-        verts = verts[mask]
-    verts = verts.view(-1, 3).contiguous()
-    vert_img_coords = torch.stack(torch.meshgrid(
-        torch.linspace(0, 1, H, device=depth.device), torch.linspace(0, 1, W, device=depth.device), indexing='xy'), dim=-1)
-    if mask is not None:
-        vert_img_coords = vert_img_coords[mask]
-    vert_img_coords = vert_img_coords.view(-1, 2).contiguous()
-    if mask is not None:
-        vertex_idx = torch.cumsum(mask.view(-1), dim=0).view(H, W) - 1
-        vertex_idx[~mask] = -1
-    else:
-        vertex_idx = torch.arange(H * W, device=depth.device, dtype=torch.int64).view(H, W)
-    upper_left = torch.stack([x.reshape(-1) for x in [vertex_idx[1:, :-1], vertex_idx[:-1, 1:], vertex_idx[:-1, :-1]]], dim=-1)
-    lower_right = torch.stack([x.reshape(-1) for x in [vertex_idx[1:, :-1], vertex_idx[1:, 1:], vertex_idx[:-1, 1:]]], dim=-1)
-    faces = torch.stack([upper_left, lower_right], dim=1).view(-1, 3)
-    faces = faces[faces.min(dim=-1).values >= 0].contiguous()
+    dev = depth.device
+    inside = torch.ones((H, W), dtype=torch.bool, device=dev) if mask is None else mask.reshape(H, W).to(dev).bool()
+    rows, cols = torch.nonzero(inside, as_tuple=True)                       # raster order = vertex order
+    world = depth_to_world_coords(depth, intrinsics=intrinsics, extrinsics_R=extrinsics_R, extrinsics_t=extrinsics_t)
+    verts = world[rows, cols].contiguous()
+    # vertex number of every pixel (-1 outside the mask), then the four corners of every 2x2 block
+    number = torch.full((H, W), -1, dtype=torch.int64, device=dev)
+    number[rows, cols] = torch.arange(rows.numel(), dtype=torch.int64, device=dev)
+    tl, tr, bl, br = number[:-1, :-1], number[:-1, 1:], number[1:, :-1], number[1:, 1:]
+    quads = torch.stack([torch.stack([bl, tr, tl], dim=-1), torch.stack([bl, br, tr], dim=-1)], dim=-2)   # (H-1, W-1, 2, 3)
+    faces = quads.reshape(-1, 3)
+    faces = faces[(faces >= 0).all(dim=-1)].contiguous()
     mesh = Mesh(verts=verts, faces=faces)
-    mesh.add_vert_attribute("color", torch.cat(
-        [vert_img_coords, torch.full_like(vert_img_coords[:, [0]], fill_value=0 if mask is None else 1)], dim=-1))
+    xs, ys = torch.linspace(0, 1, W, device=dev), torch.linspace(0, 1, H, device=dev)
+    flag = torch.full((rows.numel(),), 0.0 if mask is None else 1.0, dtype=xs.dtype, device=dev)
+    mesh.add_vert_attribute("color", torch.stack([xs[cols], ys[rows], flag], dim=-1))
     return mesh
 
 
@@ -214,13 +210,10 @@ def transform_point_cloud(points, axis, angle_degrees, x, y, z, mask):
 
 
 def _empty_mask_result(depth, use_input_depth_normalization):
-    # depth_transform.py:203-216
-    if use_input_depth_normalization:
-        _, depth_bounds = normalize_depth(1.0 / depth, return_bounds=True)
-    else:
-        depth_bounds = None
-    e = torch.tensor([], dtype=torch.int64)
-    return normalize_depth(1.0 / depth, bounds=depth_bounds), pack_correspondences(e, e, e, e)
+    """No foreground at all (depth_transform.py:203-216): the normalised input disparity and an empty (0,4) int64 list."""
+    disparity = 1.0 / depth
+    bounds = normalize_depth(disparity, return_bounds=True)[1] if use_input_depth_normalization else None
+    return normalize_depth(disparity, bounds=bounds), torch.empty((0, 4), dtype=torch.int64)
 
 
 def transform_depth_pc(depth: torch.Tensor, bg_depth: torch.Tensor, fg_mask: torch.Tensor, intrinsics: torch.Tensor,
@@ -235,18 +228,16 @@ def transform_depth_pc(depth: torch.Tensor, bg_depth: torch.Tensor, fg_mask: tor
     if not fg_mask.any():
         res = _empty_mask_result(depth, use_input_depth_normalization)
         return (*res, None) if return_device_result else res
-    if rot_angle is None:
-        rot_angle = 0.0
-    if rot_axis is None:
-        rot_axis = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float32)
-    if translation is None:
-        translation = torch.tensor([0.0, 0.0, 0.0], dtype=torch.float32)
-    if fg_mask.shape[-2] != fg_mask.shape[-1]:
-        raise RuntimeError(f'Expected fg_mask to be square, got shape {fg_mask.shape[-2]} x {fg_mask.shape[-1]}.')
-    if depth.shape[0] != 1:
-        raise ValueError("Only batch size 1 is supported")
-    _require_cuda(depth, "depth")
     S = fg_mask.shape[-1]
+    if fg_mask.shape[-2] != S:
+        raise RuntimeError(f"the 'pc' depth transform needs a square mask, got {fg_mask.shape[-2]} x {S}")
+    if depth.shape[0] != 1:
+        raise ValueError(f"one image per call (batch size 1), got a batch of {depth.shape[0]}")
+    _require_cuda(depth, "depth")
+    # defaults of the reference: no rotation about +y, no translation (depth_transform.py:219-224)
+    rot_angle = 0.0 if rot_angle is None else rot_angle
+    rot_axis = torch.tensor([0.0, 1.0, 0.0]) if rot_axis is None else rot_axis
+    translation = torch.zeros(3) if translation is None else translation
     dev = depth.device
     eng = get_engine(dev, 1, S, S)
     f32 = torch.float32
@@ -272,38 +263,27 @@ def transform_depth_mesh(depth: torch.Tensor, bg_depth: torch.Tensor, fg_mask: t
     if not fg_mask.any():
         return _empty_mask_result(depth, use_input_depth_normalization)
     _require_cuda(depth, "depth")
-    if rot_angle is None:
-        rot_angle = 0.0
-    if rot_axis is None:
-        rot_axis = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float32, device=depth.device)
-    if translation is None:
-        translation = torch.tensor([0.0, 0.0, 0.0], dtype=torch.float32, device=depth.device)
-    rot_angle = torch.tensor(float(rot_angle), dtype=torch.float32)
-    bg_mesh = depth_to_mesh(depth=bg_depth, intrinsics=intrinsics)
-    fg_mesh = depth_to_mesh(depth=depth, intrinsics=intrinsics, mask=fg_mask[0, 0] > 0.5)
-    fg_mesh.verts = transform_points(points=fg_mesh.verts, rot_angle=rot_angle, rot_axis=rot_axis, translation=translation)
-    renderer = PyTorch3DRenderer(
-        output_names=['world_position', 'flat_vertex_color'],
-        args=PyTorch3DRendererArgs(device=depth.device, output_res=(depth.shape[-2], depth.shape[-1]), cull_backfaces=True,
-                                   blur_radius=0.00001))
-    renderer.update_scene(scene_elements={'meshes': [bg_mesh, fg_mesh], 'cameras': [Camera(intrinsics=intrinsics)]})
-    out = renderer.render()
-    edited_depth = out['world_position'][None, ..., 2]
-    src = out['flat_vertex_color'][0, ..., :2]
-    edited_fg_mask = out['flat_vertex_color'][0, ..., 2] > 0.5
-    H, W = edited_depth.shape[-2], edited_depth.shape[-1]
-    dev = edited_depth.device
-    dst = torch.stack(torch.meshgrid(torch.linspace(0, 1, H, device=dev), torch.linspace(0, 1, W, device=dev), indexing='xy'), dim=-1)
-    src = src * torch.tensor([[depth.shape[-1] - 1, depth.shape[-2] - 1]], device=dev, dtype=torch.float32)
-    dst = dst * torch.tensor([[W - 1, H - 1]], device=dev, dtype=torch.float32)
-    src = torch.round(src).to(dtype=torch.int64)[edited_fg_mask].to(device='cpu')
-    dst = torch.round(dst).to(dtype=torch.int64)[edited_fg_mask].to(device='cpu')
-    correspondences = pack_correspondences(src[:, 0], src[:, 1], dst[:, 0], dst[:, 1])
-    if use_input_depth_normalization:
-        _, depth_bounds = normalize_depth(1.0 / depth, return_bounds=True)
-    else:
-        depth_bounds = None
-    return normalize_depth(1.0 / edited_depth, bounds=depth_bounds), correspondences
+    dev = depth.device
+    H, W = depth.shape[-2], depth.shape[-1]
+    angle = torch.tensor(0.0 if rot_angle is None else float(rot_angle), dtype=torch.float32)
+    axis = torch.tensor([0.0, 1.0, 0.0], device=dev) if rot_axis is None else rot_axis
+    shift = torch.zeros(3, device=dev) if translation is None else translation
+    background = depth_to_mesh(depth=bg_depth, intrinsics=intrinsics)
+    foreground = depth_to_mesh(depth=depth, intrinsics=intrinsics, mask=fg_mask[0, 0] > 0.5)
+    foreground.verts = transform_points(points=foreground.verts, rot_angle=angle, rot_axis=axis, translation=shift)
+    renderer = PyTorch3DRenderer(output_names=['world_position', 'flat_vertex_color'],
+                                 args=PyTorch3DRendererArgs(device=dev, output_res=(H, W), cull_backfaces=True, blur_radius=1e-5))
+    renderer.update_scene(scene_elements={'meshes': [background, foreground], 'cameras': [Camera(intrinsics=intrinsics)]})
+    layers = renderer.render()
+    target_depth = layers['world_position'][None, ..., 2]                   # (1,1,H,W): world z of the visible surface
+    carried = layers['flat_vertex_color'][0]                                # (H,W,4): source x/(W-1), y/(H-1), fg flag, alpha
+    # one correspondence per target pixel that shows the foreground mesh, in target raster order; the destination is the
+    # pixel itself, the source the carried normalised coordinate scaled back to pixels and rounded half-to-even
+    ty, tx = torch.nonzero(carried[..., 2] > 0.5, as_tuple=True)
+    source = torch.round(carried[ty, tx, :2] * carried.new_tensor([W - 1, H - 1])).to(torch.int64)
+    correspondences = torch.stack([source[:, 0], source[:, 1], tx, ty], dim=-1).to(device='cpu')
+    bounds = normalize_depth(1.0 / depth, return_bounds=True)[1] if use_input_depth_normalization else None
+    return normalize_depth(1.0 / target_depth, bounds=bounds), correspondences
 
 
 def transform_depth(depth: torch.Tensor, bg_depth: torch.Tensor, fg_mask: torch.Tensor, intrinsics: torch.Tensor,

@@ -74,23 +74,31 @@ class DiffusionHandles:
         N.check(lib.dh_morph_pass(N.ptr(bits), N.ptr(dil), 1, H, W, rows, 2 * r + 1, 2 * r + 1, 1, N.stream_handle(dev)), "dh_morph_pass")
         return _poisson_device(d, dil, lap_source=b)[None]
 
+    def edit_geometry(self, depth: torch.Tensor, fg_mask: torch.Tensor, bg_depth: torch.Tensor, rot_angle: float = None,
+                      rot_axis: torch.Tensor = None, translation: torch.Tensor = None, use_input_depth_normalization=False):
+        """The geometry half of an edit on the sm_100a kernels: edited disparity (1,1,H,W) and correspondences (N,4) int64."""
+        with torch.no_grad():
+            return transform_depth(depth=depth, bg_depth=bg_depth, fg_mask=fg_mask,
+                                   intrinsics=self.diffuser.get_depth_intrinsics(device=depth.device), rot_angle=rot_angle,
+                                   rot_axis=rot_axis, translation=translation,
+                                   use_input_depth_normalization=use_input_depth_normalization,
+                                   depth_transform_mode=self.conf.depth_transform_mode)
+
     def transform_foreground(self, depth: torch.Tensor, prompt: str, fg_mask: torch.Tensor, bg_depth: torch.Tensor,
                              null_text_emb: torch.Tensor, init_noise: torch.Tensor, activations: list,
                              rot_angle: float = None, rot_axis: torch.Tensor = None, translation: torch.Tensor = None,
                              fg_weight: float = None, bg_weight: float = None, use_input_depth_normalization=False):
+        """diffusion_handles.py:110-166: geometry on this package's kernels, then the injected diffuser's guided denoising.
+        Returns (edited_img, edited_disparity) plus the saved denoising steps when the configuration asks for them."""
+        guided = self._need(self.diffuser, "guided_inference")
+        disparity, correspondences = self.edit_geometry(depth, fg_mask, bg_depth, rot_angle, rot_axis, translation,
+                                                        use_input_depth_normalization)
+        keep_steps = bool(self.conf.guided_diffuser.save_denoising_steps)
         with torch.no_grad():
-            edited_disparity, correspondences = transform_depth(
-                depth=depth, bg_depth=bg_depth, fg_mask=fg_mask,
-                intrinsics=self.diffuser.get_depth_intrinsics(device=depth.device),
-                rot_angle=rot_angle, rot_axis=rot_axis, translation=translation,
-                use_input_depth_normalization=use_input_depth_normalization,
-                depth_transform_mode=self.conf.depth_transform_mode)
-        with torch.no_grad():
-            results = self._need(self.diffuser, "guided_inference")(
-                latents=init_noise, depth=edited_disparity, uncond_embeddings=null_text_emb, prompt=prompt,
-                activations_orig=activations, correspondences=correspondences, fg_weight=fg_weight, bg_weight=bg_weight,
-                save_denoising_steps=self.conf.guided_diffuser.save_denoising_steps)
-        if self.conf.guided_diffuser.save_denoising_steps:
-            edited_img, denoising_steps = results
-            return edited_img, edited_disparity, denoising_steps
-        return results, edited_disparity
+            out = guided(latents=init_noise, depth=disparity, uncond_embeddings=null_text_emb, prompt=prompt,
+                         activations_orig=activations, correspondences=correspondences, fg_weight=fg_weight,
+                         bg_weight=bg_weight, save_denoising_steps=keep_steps)
+        if keep_steps:
+            image, steps = out
+            return image, disparity, steps
+        return out, disparity

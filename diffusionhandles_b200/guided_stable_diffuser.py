@@ -58,69 +58,83 @@ def process_correspondences_device(corr: torch.Tensor, img_res: int, bg_erosion:
 
 
 class GuidanceWeightSchedule:
-    """guided_stable_diffuser.py:612-620"""
+    """Base schedule (guided_stable_diffuser.py:612-620): unit weights for the three guided layers at every step."""
 
     def __call__(self, denoising_step: int, optimization_step: int):
-        return [1.0] * 3, [1.0] * 3
+        return [1.0, 1.0, 1.0], [1.0, 1.0, 1.0]
+
+
+class _StepTable:
+    """Piecewise-constant weight table: rows (first_step, fg_weights, bg_weights); a step uses the row with the largest
+    first_step that does not exceed it."""
+
+    def __init__(self, rows, what: str):
+        rows = sorted(rows, key=lambda r: r[0])
+        for _, fg, bg in rows:
+            if len(fg) != len(bg):
+                raise ValueError("Number of foreground and background weights do not match.")
+        self.what = what
+        self.starts = [r[0] for r in rows]
+        self.weights = [(list(r[1]), list(r[2])) for r in rows]
+        self.width = len(rows[0][1])
+
+    def at(self, step: int):
+        import bisect
+        i = bisect.bisect_right(self.starts, step) - 1
+        return self.weights[i] if i >= 0 else None
 
 
 class StepGuidanceWeightSchedule(GuidanceWeightSchedule):
-    """guided_stable_diffuser.py:622-665"""
+    """guided_stable_diffuser.py:622-665: per-layer weights = (weights of the denoising step) x (weights of the optimisation
+    iteration), each looked up in a piecewise-constant table.  Same constructor arguments and errors as the reference."""
 
     def __init__(self, denoising_steps, optimization_steps):
-        super().__init__()
-        if not all(len(fg) == len(bg) for _, fg, bg in denoising_steps):
-            raise ValueError("Number of foreground and background weights do not match.")
-        if not all(len(fg) == len(bg) for _, fg, bg in optimization_steps):
-            raise ValueError("Number of foreground and background weights do not match.")
-        if len(denoising_steps[0][1]) != len(optimization_steps[0][1]):
+        self._denoising = _StepTable(denoising_steps, "denoising")
+        self._optimization = _StepTable(optimization_steps, "optimization")
+        if self._denoising.width != self._optimization.width:
             raise ValueError("Number of denoising and optimization weights do not match.")
-        self.denoising_steps = sorted(denoising_steps, key=lambda step: step[0])
-        self.optimization_steps = sorted(optimization_steps, key=lambda step: step[0])
+        self.denoising_steps = list(zip(self._denoising.starts, *zip(*self._denoising.weights)))
+        self.optimization_steps = list(zip(self._optimization.starts, *zip(*self._optimization.weights)))
 
     def __call__(self, denoising_step: int, optimization_step: int):
-        d = o = None
-        for step, fg, bg in reversed(self.denoising_steps):
-            if denoising_step >= step:
-                d = (fg, bg)
-                break
-        for step, fg, bg in reversed(self.optimization_steps):
-            if optimization_step >= step:
-                o = (fg, bg)
-                break
-        if d is None or o is None:
+        den, opt = self._denoising.at(denoising_step), self._optimization.at(optimization_step)
+        if den is None or opt is None:
             raise ValueError(f"Could not find weights for denoising step {denoising_step} and optimization step {optimization_step}.")
-        return [a * b for a, b in zip(d[0], o[0])], [a * b for a, b in zip(d[1], o[1])]
+        return [d * o for d, o in zip(den[0], opt[0])], [d * o for d, o in zip(den[1], opt[1])]
+
+
+# guided_stable_diffuser.py:336-373 - which of the three guided layers is active in denoising step t (t mod 3), and the
+# multipliers of the optimisation iterations 0..3
+_LAYER_PATTERN = (((0.0, 0.0, 7.5), (0.0, 0.0, 1.5)),
+                  ((0.0, 5.0, 0.0), (0.0, 1.5, 0.0)),
+                  ((0.0, 5.0, 7.5), (0.0, 1.5, 1.5)))
+_ITERATION_GAIN = ((2.5, 1.25), (1.25, 2.5), (1.25, 1.25), (2.5, 2.5))
+
+
+def _fade(weight: float, steps: int, kind: str) -> np.ndarray:
+    """Weight over the guided denoising steps: constant, linear to zero, or quadratic to zero (np.linspace like the reference)."""
+    if kind == "constant":
+        return np.linspace(weight, weight, steps)
+    if kind == "linear":
+        return np.linspace(weight, 0.0, steps)
+    if kind == "quadratic":
+        return np.linspace(np.sqrt(weight), 0.0, steps) ** 2
+    raise ValueError(f"Unknown guidance schedule type: {kind}")
 
 
 def make_guidance_weight_schedule(fg_weight: float, bg_weight: float, guidance_max_step: int = 38,
                                   guidance_schedule_type: str = "constant") -> StepGuidanceWeightSchedule:
-    """guided_stable_diffuser.py:336-373."""
-    fg_weight = fg_weight * 30
-    bg_weight = bg_weight * 30
-    if guidance_schedule_type == "constant":
-        ff = np.linspace(fg_weight, fg_weight, guidance_max_step)
-        bf = np.linspace(bg_weight, bg_weight, guidance_max_step)
-    elif guidance_schedule_type == "linear":
-        ff = np.linspace(fg_weight, 0.0, guidance_max_step)
-        bf = np.linspace(bg_weight, 0.0, guidance_max_step)
-    elif guidance_schedule_type == "quadratic":
-        ff = np.linspace(np.sqrt(fg_weight), 0.0, guidance_max_step) ** 2
-        bf = np.linspace(np.sqrt(bg_weight), 0.0, guidance_max_step) ** 2
-    else:
-        raise ValueError(f"Unknown guidance schedule type: {guidance_schedule_type}")
-    den = []
-    for t_idx in range(guidance_max_step):
-        if t_idx % 3 == 0:
-            fw, bw = [0.0, 0.0, 7.5], [0.0, 0.0, 1.5]
-        elif t_idx % 3 == 1:
-            fw, bw = [0.0, 5.0, 0.0], [0.0, 1.5, 0.0]
-        else:
-            fw, bw = [0.0, 5.0, 7.5], [0.0, 1.5, 1.5]
-        den.append((t_idx, (np.array(fw) * ff[t_idx]).tolist(), (np.array(bw) * bf[t_idx]).tolist()))
-    den.append((guidance_max_step, [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]))
-    opt = [(0, [2.5] * 3, [1.25] * 3), (1, [1.25] * 3, [2.5] * 3), (2, [1.25] * 3, [1.25] * 3), (3, [2.5] * 3, [2.5] * 3)]
-    return StepGuidanceWeightSchedule(denoising_steps=den, optimization_steps=opt)
+    """The schedule ``guided_inference`` builds (guided_stable_diffuser.py:336-373): user weights x 30, faded over the first
+    ``guidance_max_step`` denoising steps, distributed over the layers by ``t mod 3``, zero afterwards."""
+    fg_fade = _fade(fg_weight * 30, guidance_max_step, guidance_schedule_type)
+    bg_fade = _fade(bg_weight * 30, guidance_max_step, guidance_schedule_type)
+    denoising = []
+    for t in range(guidance_max_step):
+        fg_pat, bg_pat = _LAYER_PATTERN[t % 3]
+        denoising.append((t, (np.array(fg_pat) * fg_fade[t]).tolist(), (np.array(bg_pat) * bg_fade[t]).tolist()))
+    denoising.append((guidance_max_step, [0.0] * 3, [0.0] * 3))
+    optimization = [(i, [f] * 3, [b] * 3) for i, (f, b) in enumerate(_ITERATION_GAIN)]
+    return StepGuidanceWeightSchedule(denoising_steps=denoising, optimization_steps=optimization)
 
 
 class GuidedStableDiffuser:
