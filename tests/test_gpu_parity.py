@@ -861,7 +861,8 @@ def test_randomised_parity_sweep(dev):
     """80 random edits (sizes 64..512, disc and smooth scenes, quantised depths, axis-aligned and general axes, large
     translations that push points off screen or behind the camera, both normalisation modes): every intermediate of the
     geometry path bit-exact against the oracle.  tools/fuzz_parity.py runs the same sweep at any length (2,500 cases clean)."""
+    import os
     import sys
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_parity
     assert fuzz_parity.run(80, seed=7, verbose=True) == 0
