@@ -460,9 +460,10 @@ __global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_con
     }
     __syncthreads();
     if (tid < h) {       // up rows that touch native row tid, and their weights
+        // (taps with weight zero - the clamped rows at the top border have i1 = 1 with lambda = 0 - are not part of the window)
         int lo = G, hi = -1;
         for (int r = 0; r < G; ++r)
-            if (T.ty0[r] == tid || T.ty1[r] == tid) { lo = min(lo, r); hi = max(hi, r); }
+            if ((T.ty0[r] == tid && T.tly[r] < 1.0f) || (T.ty1[r] == tid && T.tly[r] > 0.0f)) { lo = min(lo, r); hi = max(hi, r); }
         hi = min(hi, lo + kWin - 1);
         T.ylo[tid] = lo; T.yhi[tid] = hi;
         for (int r = lo; r <= hi; ++r)
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_con
         const int j = tid - 64;
         int lo = G, hi = -1;
         for (int s = 0; s < G; ++s)
-            if (T.tx0[s] == j || T.tx1[s] == j) { lo = min(lo, s); hi = max(hi, s); }
+            if ((T.tx0[s] == j && T.tlx[s] < 1.0f) || (T.tx1[s] == j && T.tlx[s] > 0.0f)) { lo = min(lo, s); hi = max(hi, s); }
         hi = min(hi, lo + kWin - 1);
         T.xlo[j] = lo; T.xhi[j] = hi;
         for (int s = lo; s <= hi; ++s)
@@ -786,6 +787,7 @@ int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int
     DH_REQUIRE(plan && tables && grid >= 1 && grid <= kMaxG && h >= 1 && w >= 1 && n_fg >= 0);
     if (h > grid || w > grid || h > kMaxNative || w > kMaxNative) return DH_ERR_UNSUPPORTED;
     if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
+    if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
     SetupParams sp;
     sp.plan = plan; sp.plan_cap = n_fg; sp.G = grid; sp.h = h; sp.w = w; sp.fg_kind = fg_kind; sp.bg_kind = bg_kind;
     loss_resize_setup_kernel<<<1, 256, 0, as_stream(stream)>>>(sp, static_cast<LayerTab*>(tables));
@@ -820,6 +822,8 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         const dh_loss_layer& s = layers_host[i];
         DH_REQUIRE(s.cur && s.orig && s.channels >= 1 && s.h >= 1 && s.w >= 1);
         if (s.h > kMaxNative || s.w > kMaxNative || s.h > grid || s.w > grid) return DH_ERR_UNSUPPORTED;
+        // the transposed-resize tables hold kWin up rows (columns) per native row (column): 2 * ceil(grid / h) of them are needed
+        if (2 * ((grid + s.h - 1) / s.h) > kWin || 2 * ((grid + s.w - 1) / s.w) > kWin) return DH_ERR_UNSUPPORTED;
         if (((size_t)s.h * s.w) % 4 != 0) return DH_ERR_UNSUPPORTED;     // 128-bit plane loads
         if ((reinterpret_cast<uintptr_t>(s.cur) & 15) || (reinterpret_cast<uintptr_t>(s.orig) & 15) ||
             (s.grad && (reinterpret_cast<uintptr_t>(s.grad) & 15)))

@@ -110,7 +110,9 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
         raise N.NativeLibraryError("guidance losses run on CUDA only; there is no CPU fallback")
     L = len(curs)
     shapes = tuple(tuple(c.shape) for c in curs)
-    key = (shapes, fg_kind, bg_kind, patch)
+    # maps smaller than grid/8 (e.g. 4x4) exceed the tap window of the specialised patch-1 kernels: the general kernel takes them
+    general = patch != 1 or any(2 * -(-plan.grid // min(sh[1], sh[2])) > 16 for sh in shapes)
+    key = (shapes, fg_kind, bg_kind, patch, general)
     runner = plan._runners.get(key)
     if runner is None:
         # per (plan, shapes): the ctypes layer array, the workspace and the resize tables are created once
@@ -124,11 +126,11 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
             if sh[1] > plan.grid or sh[2] > plan.grid:
                 raise NotImplementedError(f"activation maps larger than the loss grid ({sh[1]}x{sh[2]} > {plan.grid}) are not implemented")
             t = None
-            if patch == 1 and (sh[1], sh[2]) != (plan.grid, plan.grid):
+            if not general and (sh[1], sh[2]) != (plan.grid, plan.grid):
                 t = plan.resize_tables(sh[1], sh[2], fg_kind, bg_kind)
             tabs.append(t)
             layers[i].resize_tables = N.ptr(t) if t is not None else None
-        ws_fn = lib.dh_guidance_loss_workspace_bytes if patch == 1 else lib.dh_guidance_loss_patch_workspace_bytes
+        ws_fn = lib.dh_guidance_loss_patch_workspace_bytes if general else lib.dh_guidance_loss_workspace_bytes
         ws_bytes = int(ws_fn(L, max(sh[0] for sh in shapes)))
         runner = (layers, torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes, tabs)
         plan._runners[key] = runner
@@ -148,7 +150,7 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
     out = torch.empty(1 + 2 * L, dtype=torch.float32, device=dev)
     n_fg, n_bo, n_bt, n_bc = plan.n
     st = N.stream_handle(dev)
-    if patch == 1:
+    if not general:
         N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
                                      fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
     else:

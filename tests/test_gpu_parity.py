@@ -411,7 +411,7 @@ def test_fused_guidance_loss_with_patches(dev, golden_pc):
         dcur, dorig = [c.to(dev) for c in curs], [o.to(dev) for o in origs]
         o1, g1 = losses._launch(dcur, dorig, [True] * 3, fgw, bgw, plan, 1, kind, 1)
         lib = losses.N.load()
-        runner_key = (tuple(tuple(c.shape) for c in dcur), 1, kind, 1)
+        runner_key = (tuple(tuple(c.shape) for c in dcur), 1, kind, 1, False)
         layers, _, _, _ = plan._runners[runner_key]
         g2 = [torch.empty_like(c) for c in dcur]
         for i in range(3):
@@ -866,3 +866,14 @@ def test_randomised_parity_sweep(dev):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_parity
     assert fuzz_parity.run(80, seed=7, verbose=True) == 0
+
+
+def test_randomised_loss_sweep(dev):
+    """60 random loss evaluations (index lists with duplicates from 1 to 20,000 entries, maps from 4x4 to 64x64 including
+    non-square and non-power-of-two sizes, both background types, patch sizes 1..5) against the fp64 oracle; this sweep
+    found the tap-window bug of 8x8 maps.  tools/fuzz_losses.py runs it at any length."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_losses
+    assert fuzz_losses.run(60, seed=11, verbose=True) == 0
