@@ -888,3 +888,14 @@ def test_randomised_misc_sweep(dev):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_misc
     assert fuzz_misc.run(40, seed=13, verbose=True) == 0
+
+
+def test_randomised_batch_poisson_raster_sweep(dev):
+    """12 random cases each of: batched edits with mixed / empty masks (per-edit results bit-exact), edits with the Poisson
+    hole fill (1e-3 on the 0..255 disparity vs SuperLU), and the triangle rasteriser on random meshes with random culling /
+    blur settings (bit-exact vs the NumPy restatement).  tools/fuzz_more.py runs it at any length (600 cases clean)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_more
+    assert fuzz_more.run(12, seed=17, verbose=True) == 0
