@@ -618,11 +618,14 @@ def foreground_loss(cur: np.ndarray, orig: np.ndarray, pc: Dict[str, np.ndarray]
         den2 = (box_sum(w2, patch) / pp + dtype(1e-10)).astype(dtype)
         uo = ((box_sum(w1 * uo, patch) / pp).astype(dtype) / den1).astype(dtype)
         uc = ((box_sum(w2 * uc, patch) / pp).astype(dtype) / den2).astype(dtype)
-    d = uo[:, ys, xs] - uc[:, yd, xd]
+    # patch 1: the local average of an indexed cell is f / (1 + 1e-10) (losses.py:75-77) - the identity in fp32, a 1e-10
+    # relative factor in fp64
+    one_eps = dtype(1) + dtype(1e-10) if patch == 1 else dtype(1)
+    d = uo[:, ys, xs] / one_eps - uc[:, yd, xd] / one_eps
     loss = np.abs(d).mean(axis=-1).mean()
     g_up = np.zeros((C, size[0] * size[1]), dtype)
     cell = yd * size[1] + xd
-    contrib = -np.sign(d) / dtype(C * N)
+    contrib = -np.sign(d) / dtype(C * N) / one_eps
     for c in range(C) if C <= 8 else ():
         np.add.at(g_up[c], cell, contrib[c])
     if C > 8:
