@@ -1,6 +1,6 @@
 """Randomised parity sweep of the guidance losses (K4, both kernels) against the fp64 oracle: random index lists with
 duplicates, random layer shapes (including non-square and non-power-of-two maps), both background types, patch sizes 1..5.
-python tools/fuzz_losses.py [n_cases] [seed]"""
+python tests/fuzz/fuzz_losses.py [n_cases] [seed]"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import dh_oracle as O                                        # noqa: E402
 from diffusionhandles_b200 import losses                                 # noqa: E402
 

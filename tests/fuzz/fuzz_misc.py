@@ -2,7 +2,7 @@
   p2d    points_to_depth on arbitrary fp64 point sets (duplicates, exact z ties, points behind the camera, off-screen, NaN z)
   pcorr  process_correspondences (random lists, image sizes, erosion, out-of-bounds entries)
   warp   gather_list / warp_stacks on random shapes (TMA fast path and the generic path) against torch indexing
-python tools/fuzz_misc.py [n_cases] [seed]"""
+python tests/fuzz/fuzz_misc.py [n_cases] [seed]"""
 import os
 import sys
 import time
@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import dh_oracle as O                                        # noqa: E402
 from diffusionhandles_b200 import depth_transform as dt, warp           # noqa: E402
 from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser   # noqa: E402

@@ -4,7 +4,7 @@
   poisson  edits with the Poisson hole fill, |disparity - oracle (SuperLU)| <= 1e-3 on the 0..255 scale
   raster   the triangle rasteriser on random depth-map meshes (sizes 16..48, random rigid moves): pix_to_face, zbuf,
            barycentrics bit-exact against the NumPy restatement of pytorch3d's semantics
-python tools/fuzz_more.py [n_cases] [seed]"""
+python tests/fuzz/fuzz_more.py [n_cases] [seed]"""
 import os
 import sys
 import time
@@ -12,7 +12,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import dh_oracle as O                                        # noqa: E402
 from diffusionhandles_b200 import depth_transform as dt                 # noqa: E402
 from diffusionhandles_b200.engine import EditEngine, make_rigid          # noqa: E402

@@ -1,6 +1,6 @@
 """CPU only, where /root/reference exists: the oracle against the REAL reference on random inputs (beyond the committed
 golden vectors).  transform_depth_pc (512^2, the reference is hard-wired to that size), process_correspondences, losses.
-python tools/fuzz_oracle_vs_reference.py [n_cases] [seed]"""
+python tests/fuzz/fuzz_oracle_vs_reference.py [n_cases] [seed]"""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ import warnings
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import dh_oracle as O                                        # noqa: E402
 from oracle.ref_loader import load_reference                             # noqa: E402
 

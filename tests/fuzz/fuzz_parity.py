@@ -1,5 +1,5 @@
 """Randomised parity sweep: CUDA path vs the oracle on random scenes / transforms (bit-exact comparison of the splat winners,
-depth maps, masks, correspondences).  python tools/fuzz_parity.py [n_cases] [seed]"""
+depth maps, masks, correspondences).  python tests/fuzz/fuzz_parity.py [n_cases] [seed]"""
 import os
 import sys
 import time
@@ -7,8 +7,8 @@ import time
 import numpy as np
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from oracle import dh_oracle as O                                        # noqa: E402
 from diffusionhandles_b200.engine import get_engine, make_rigid          # noqa: E402
 from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser   # noqa: E402

@@ -860,10 +860,10 @@ def test_general_rotation_axis_matches_the_oracle(dev, K, axis, angle):
 def test_randomised_parity_sweep(dev):
     """80 random edits (sizes 64..512, disc and smooth scenes, quantised depths, axis-aligned and general axes, large
     translations that push points off screen or behind the camera, both normalisation modes): every intermediate of the
-    geometry path bit-exact against the oracle.  tools/fuzz_parity.py runs the same sweep at any length (2,500 cases clean)."""
+    geometry path bit-exact against the oracle.  tests/fuzz/fuzz_parity.py runs the same sweep at any length (2,500 cases clean)."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
     import fuzz_parity
     assert fuzz_parity.run(80, seed=7, verbose=True) == 0
 
@@ -871,10 +871,10 @@ def test_randomised_parity_sweep(dev):
 def test_randomised_loss_sweep(dev):
     """60 random loss evaluations (index lists with duplicates from 1 to 20,000 entries, maps from 4x4 to 64x64 including
     non-square and non-power-of-two sizes, both background types, patch sizes 1..5) against the fp64 oracle; this sweep
-    found the tap-window bug of 8x8 maps.  tools/fuzz_losses.py runs it at any length."""
+    found the tap-window bug of 8x8 maps.  tests/fuzz/fuzz_losses.py runs it at any length."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
     import fuzz_losses
     assert fuzz_losses.run(60, seed=11, verbose=True) == 0
 
@@ -882,10 +882,10 @@ def test_randomised_loss_sweep(dev):
 def test_randomised_misc_sweep(dev):
     """40 random cases each of points_to_depth (duplicates, exact z ties, points behind the camera, off-screen), of
     process_correspondences (sizes 64..1024, erosion, out-of-bounds destinations) and of the warp gathers (TMA fast path
-    and generic shapes, empty index lists); bit-exact.  tools/fuzz_misc.py runs it at any length (3,000 cases clean)."""
+    and generic shapes, empty index lists); bit-exact.  tests/fuzz/fuzz_misc.py runs it at any length (3,000 cases clean)."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
     import fuzz_misc
     assert fuzz_misc.run(40, seed=13, verbose=True) == 0
 
@@ -893,9 +893,9 @@ def test_randomised_misc_sweep(dev):
 def test_randomised_batch_poisson_raster_sweep(dev):
     """12 random cases each of: batched edits with mixed / empty masks (per-edit results bit-exact), edits with the Poisson
     hole fill (1e-3 on the 0..255 disparity vs SuperLU), and the triangle rasteriser on random meshes with random culling /
-    blur settings (bit-exact vs the NumPy restatement).  tools/fuzz_more.py runs it at any length (600 cases clean)."""
+    blur settings (bit-exact vs the NumPy restatement).  tests/fuzz/fuzz_more.py runs it at any length (600 cases clean)."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
     import fuzz_more
     assert fuzz_more.run(12, seed=17, verbose=True) == 0
