@@ -115,3 +115,24 @@ def test_product_and_oracle_scene_generators_agree():
     for kw in (dict(S=64, seed=3), dict(S=128, seed=5, cx=40.0, cy=70.0, radius=30.0, quantize=0.1)):
         for a, b in zip(synthetic_scene(**kw), O.synthetic_scene(**kw)):
             assert np.array_equal(a, b)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under diffusionhandles_b200/ may import or mention it, and the only other
+    files that do are tests/, __graft_entry__.py (smoke) and bench.py (CPU legs)."""
+    pkg = os.path.join(ROOT, "diffusionhandles_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    text = fh.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for f in os.listdir(ROOT):
+        if f.endswith(".py") and f not in allowed:
+            with open(os.path.join(ROOT, f)) as fh:
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", fh.read(), flags=re.M), f"{f} imports the oracle"
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            with open(os.path.join(ROOT, "tools", f)) as fh:
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", fh.read(), flags=re.M), f"tools/{f} imports the oracle"
