@@ -136,6 +136,20 @@ def config4():
                 warp.dense_source_maps(r.corr, r.n_corr, 512, [64, 32, 16, 8], r.winner_src)
         med, mn = timeit(sweep, n=5, warm=2)
         print(json.dumps({"config": "config4_geometry_sweep", "chunk": chunk, "edits": 256, "ms_per_sweep": med, "edits_per_s": 256 / med * 1e3}), flush=True)
+        if chunk == 64:
+            # the whole device-resident pipeline: geometry -> dense maps -> K3 warp of every edit's own config-2 stack
+            levels = [torch.randn((256, c, s_, s_), device=dev) for c, s_ in bench.LEVELS]
+            outs = [torch.empty_like(l) for l in levels]
+
+            def full():
+                for e0 in range(0, 256, chunk):
+                    r = eng.run(d[e0:e0 + chunk], b[e0:e0 + chunk], m[e0:e0 + chunk], K, rg[e0:e0 + chunk], poisson=False, sync_counts=False)
+                    maps = warp.dense_source_maps(r.corr, r.n_corr, 512, [s_ for _, s_ in bench.LEVELS], r.winner_src)
+                    warp.warp_stacks([l[e0:e0 + chunk] for l in levels], maps, [o[e0:e0 + chunk] for o in outs])
+            med, mn = timeit(full, n=5, warm=2)
+            print(json.dumps({"config": "config4_full_pipeline_device_resident", "chunk": chunk, "edits": 256, "ms_per_sweep": med,
+                              "edits_per_s": 256 / med * 1e3, "what": "K1,K2,masks,correspondences,dense maps,K3 per edit; inputs and stacks in HBM"}), flush=True)
+            del levels, outs
         del eng
 
 
