@@ -292,17 +292,22 @@ __global__ void __launch_bounds__(256) dense_maps_scatter_kernel(const int64_t* 
             if (l >= lv.n_levels) break;
             const int side = lv.side[l], r = lv.img_res / side;
             const int d = (int)(v.w / r) * side + (int)(v.z / r);
-            atomicMin(maps + lv.map_begin[l] + (size_t)e * side * side + d, n);
+            int32_t* cell = maps + lv.map_begin[l] + (size_t)e * side * side + d;
+            // the map only ever decreases, so a plain (possibly stale) read can only over-estimate it: skipping when n is not
+            // below it is conservative.  Coarse levels have hundreds of correspondences per cell - almost all of them skip.
+            if (n < __ldcg(cell)) atomicMin(cell, n);
         }
     }
 }
 
-// one warp per (level, destination cell)
+// one thread per (level, destination cell): cells with a correspondence read its source; the others fall back to the first
+// target pixel of the cell (raster order) that has a splat winner - almost always the very first one, the background covers
+// the image - so a sequential scan per thread beats a cooperative one by keeping 32x more cells in flight
 __global__ void __launch_bounds__(256) dense_maps_finalize_kernel(const int64_t* __restrict__ corr, int corr_stride_rows,
                                                                   const int32_t* __restrict__ winner_src,
                                                                   const __grid_constant__ MapLevels lv, int32_t* __restrict__ maps) {
     const int e = blockIdx.y;
-    const int gcell = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const int gcell = blockIdx.x * blockDim.x + threadIdx.x;
     if (gcell >= lv.cell_begin[lv.n_levels]) return;
     int l = 0;
 #pragma unroll
@@ -317,20 +322,16 @@ __global__ void __launch_bounds__(256) dense_maps_finalize_kernel(const int64_t*
         res = (int)(v.y / r) * side + (int)(v.x / r);
     } else if (winner_src) {
         const int cy = cell / side, cx = cell - cy * side;
-        const int32_t* ws = winner_src + (size_t)e * img_res * img_res;
-        const int n = r * r;
-        for (int k0 = 0; k0 < n && res < 0; k0 += 32) {
-            const int k = k0 + lane_id();
-            int s_ = -1;
-            if (k < n) s_ = ws[(cy * r + k / r) * img_res + cx * r + k % r];
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, s_ >= 0);
-            if (b) {
-                s_ = __shfl_sync(0xFFFFFFFFu, s_, __ffs(b) - 1);
-                res = ((s_ / img_res) / r) * side + (s_ % img_res) / r;
+        const int32_t* ws = winner_src + (size_t)e * img_res * img_res + (size_t)(cy * r) * img_res + cx * r;
+        for (int dy = 0; dy < r && res < 0; ++dy) {
+            const int32_t* row = ws + (size_t)dy * img_res;
+            for (int dx = 0; dx < r; ++dx) {
+                const int s_ = __ldg(row + dx);
+                if (s_ >= 0) { res = ((s_ / img_res) / r) * side + (s_ % img_res) / r; break; }
             }
         }
     }
-    if (lane_id() == 0) *m = res;
+    *m = res;
 }
 
 }  // namespace dh
@@ -457,7 +458,7 @@ int dh_dense_source_maps(const int64_t* corr, const int32_t* n_corr, int corr_st
     if (gx > 64) gx = 64;                         // grid-stride: the capacity is P rows, the lists are ~10x shorter
     dense_maps_scatter_kernel<<<dim3(gx, B), 256, 0, st>>>(corr, n_corr, corr_stride_rows, lv, maps);
     DH_LAUNCH_CHECK();
-    dense_maps_finalize_kernel<<<dim3((cells + 7) / 8, B), 256, 0, st>>>(corr, corr_stride_rows, winner_src, lv, maps);
+    dense_maps_finalize_kernel<<<dim3((cells + 255) / 256, B), 256, 0, st>>>(corr, corr_stride_rows, winner_src, lv, maps);
     DH_LAUNCH_CHECK();
     return DH_OK;
 }
