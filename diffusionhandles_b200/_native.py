@@ -55,12 +55,16 @@ _SIGNATURES = {
     "dh_unproject_transform_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(dh_camera),
                                                C.POINTER(dh_rigid), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dh_unproject_transform_project_splat": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(dh_camera),
+                                                     C.POINTER(dh_rigid), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_transform_point_cloud_workspace_bytes": (c_size_t, [c_int]),
     "dh_transform_point_cloud": (c_int, [c_void_p, c_void_p, c_int, C.POINTER(dh_rigid), c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_size_t, c_void_p]),
     "dh_project_points": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(dh_camera), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "dh_splat_zbuffer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dh_splat_winner": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dh_splat_resolve": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dh_splat_visible": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -224,6 +224,17 @@ int dh_splat_zbuffer(const int32_t* pix, const uint64_t* zkey, const int32_t* n_
     return DH_OK;
 }
 
+int dh_splat_winner(const int32_t* pix, const uint64_t* zkey, const int32_t* n_points, int n_fixed, int n_max,
+                    int stride_points, int B, int P, const uint64_t* zbuf, uint32_t* winner, void* stream) {
+    DH_REQUIRE(pix && zkey && zbuf && winner && B >= 1 && P >= 1 && n_max >= 0 && stride_points >= n_max);
+    cudaStream_t st = as_stream(stream);
+    DH_CUDA_CHECK(cudaMemsetAsync(winner, 0xFF, sizeof(uint32_t) * (size_t)B * P, st));
+    if (n_max == 0) return DH_OK;
+    splat_winner_kernel<<<dim3((n_max + 255) / 256, B), 256, 0, st>>>(pix, zkey, n_points, n_fixed, stride_points, P, zbuf, winner);
+    DH_LAUNCH_CHECK();
+    return DH_OK;
+}
+
 int dh_splat_resolve(const uint64_t* zbuf, const uint32_t* winner, int B, int H, int W, int fg_start,
                      const uint8_t* point_mask, const int32_t* fg_index, int stride_points, float* depth_map,
                      uint8_t* target_mask, uint32_t* target_bits, int32_t* winner_src, float* inv_minmax, void* stream) {

@@ -169,13 +169,14 @@ class EditEngine:
         cam = N.make_camera(intrinsics)
         rg = (N.dh_rigid * B)(*rigids)
         f32 = torch.float32
-        N.check(lib.dh_unproject_transform_project(
+        # K1 with pass 1 of the splat fused in (the z keys go straight into the z-buffer), then pass 2 (winner among ties)
+        N.check(lib.dh_unproject_transform_project_splat(
             N.ptr(depth, f32, "depth"), N.ptr(bg_depth, f32, "bg_depth"), N.ptr(fg_mask, f32, "fg_mask"), B, H, W,
             C.byref(cam), rg, N.ptr(self.xs), N.ptr(self.ys), N.ptr(self.pix), N.ptr(self.zkey), N.ptr(self.fg_index),
             N.ptr(self.n_fg), N.ptr(self.centroid), N.ptr(self.points) if self.points is not None else None,
-            N.ptr(self.ws), self.ws_bytes, st), "dh_unproject_transform_project")
-        N.check(lib.dh_splat_zbuffer(N.ptr(self.pix), N.ptr(self.zkey), N.ptr(self.n_fg), P, 2 * P, 2 * P, B, P,
-                                     N.ptr(self.zbuf), N.ptr(self.winner), st), "dh_splat_zbuffer")
+            N.ptr(self.zbuf), N.ptr(self.ws), self.ws_bytes, st), "dh_unproject_transform_project_splat")
+        N.check(lib.dh_splat_winner(N.ptr(self.pix), N.ptr(self.zkey), N.ptr(self.n_fg), P, 2 * P, 2 * P, B, P,
+                                    N.ptr(self.zbuf), N.ptr(self.winner), st), "dh_splat_winner")
         N.check(lib.dh_splat_resolve(N.ptr(self.zbuf), N.ptr(self.winner), B, H, W, P, None, N.ptr(self.fg_index), 2 * P,
                                      N.ptr(self.depth_map), N.ptr(self.target_mask), N.ptr(self.target_bits),
                                      N.ptr(self.winner_src), N.ptr(self.inv_minmax), st), "dh_splat_resolve")

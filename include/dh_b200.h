@@ -120,6 +120,16 @@ int dh_transform_point_cloud(const float* points, const float* mask, int N, cons
 int dh_project_points(const double* points, int N, int H, int W, const dh_camera* cam_host,
                       int32_t* pix, uint64_t* zkey, int32_t* u, int32_t* v, void* stream);
 
+/* K1 fused with pass 1 of the z-buffer splat: as above, and zbuf[e][q] = min over the edit's points that land on pixel q of
+ * the order-preserving z key (zbuf is initialised here).  Follow it with dh_splat_winner (pass 2).  The kernel is bound by
+ * its fp64 arithmetic, so the atomics cost nothing extra and one read of pix / zkey is saved. */
+int dh_unproject_transform_project_splat(const float* depth, const float* bg_depth, const float* fg_mask,
+                                         int B, int H, int W, const dh_camera* cam_host, const dh_rigid* rigid_host,
+                                         const float* xs, const float* ys,
+                                         int32_t* pix, uint64_t* zkey, int32_t* fg_index, int32_t* n_fg,
+                                         float* centroid, double* points_out, uint64_t* zbuf,
+                                         void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K2, row 5: deterministic z-buffer splat, depth_transform.py:689-712 ---------------------------
  * winner[q] = argmin over {i : pix_i = q} of (z_i, i).  Two 64/32-bit atomicMin passes (z bits, then
  * point index among the points that tie on z) - exact for fp64 depths.
@@ -128,6 +138,12 @@ int dh_project_points(const double* points, int N, int H, int W, const dh_camera
 int dh_splat_zbuffer(const int32_t* pix, const uint64_t* zkey, const int32_t* n_points, int n_fixed,
                      int n_max, int stride_points, int B, int P,
                      uint64_t* zbuf, uint32_t* winner, void* stream);
+
+/* Pass 2 alone (winner index among the points whose key equals zbuf), for a zbuf produced by
+ * dh_unproject_transform_project_splat.  Same arguments as dh_splat_zbuffer. */
+int dh_splat_winner(const int32_t* pix, const uint64_t* zkey, const int32_t* n_points, int n_fixed,
+                    int n_max, int stride_points, int B, int P,
+                    const uint64_t* zbuf, uint32_t* winner, void* stream);
 
 /* ---- K2 epilogue, rows 5-6: depth_transform.py:714-747, :283-306 ----------------------------------
  * depth_map fp32 (+inf = empty), target_mask uint8 {0,1} = winner is a foreground point,
