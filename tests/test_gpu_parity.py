@@ -899,3 +899,58 @@ def test_randomised_batch_poisson_raster_sweep(dev):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz"))
     import fuzz_more
     assert fuzz_more.run(12, seed=17, verbose=True) == 0
+
+
+def test_edit_warp_pipeline_host_buffers(dev, K):
+    """The public batched call of the e2e bench leg (batch.EditWarpPipeline.run_host): pinned HOST depth / mask / stacks in,
+    warped stacks and correspondence counts out, chunks overlapped on a ring of streams - against the oracle per edit."""
+    from diffusionhandles_b200.batch import EditWarpPipeline
+    from diffusionhandles_b200.engine import make_rigid
+    S, E = 128, 8
+    levels = [(6, 64), (5, 32), (4, 16), (3, 8)]
+    rng = np.random.default_rng(3)
+    scenes = [O.synthetic_scene(S, 70 + i, kind="smooth" if i % 3 == 0 else "disc") for i in range(E)]
+    edits = [(float(rng.uniform(-60, 60)), (0.0, 1.0, 0.0), tuple(float(v) for v in rng.normal(size=3) * 0.2)) for _ in range(E)]
+    pin = lambda a: torch.from_numpy(np.stack(a)).pin_memory()
+    depth_h, bg_h, mask_h = pin([s[0] for s in scenes]), pin([s[1] for s in scenes]), pin([s[2] for s in scenes])
+    g = torch.Generator().manual_seed(5)
+    levels_h = [torch.randn((E, c, s, s), generator=g).pin_memory() for c, s in levels]
+    outs_h = [torch.empty((E, c, s, s)).pin_memory() for c, s in levels]
+    n_corr_h = torch.empty(E, dtype=torch.int32).pin_memory()
+    pipe = EditWarpPipeline(dev, S, levels, chunk=2, n_streams=3, full_winner_map=True)
+    rigids = [make_rigid(a, list(ax), list(t)) for a, ax, t in edits]
+    for _ in range(2):                                   # twice: slot reuse across calls
+        pipe.run_host(depth_h, bg_h, mask_h, K, rigids, levels_h, outs_h, n_corr_h)
+    for e, ((depth, bg, mask), (a, ax, t)) in enumerate(zip(scenes, edits)):
+        o = O.transform_depth_pc(depth, bg, mask, K_NP, a, ax, f32_translation(t), poisson=False)
+        assert int(n_corr_h[e]) == o["correspondences"].shape[0]
+        P = S * S
+        ws = np.where(o["winner"] < 0, -1, np.where(o["winner"] < P, o["winner"], 0))
+        fgw = o["winner"] >= P
+        ws[fgw] = o["fg_index"][o["winner"][fgw] - P]
+        for (c, s), lv, out in zip(levels, levels_h, outs_h):
+            m = O.dense_source_map(o["correspondences"], S, s, ws)
+            ref = O.warp_gather_dense(lv[e].numpy(), m)
+            assert np.array_equal(out[e].numpy(), ref), (e, s)
+    with pytest.raises(ValueError):
+        pipe.run_host(depth_h[:3], bg_h[:3], mask_h[:3], K, rigids[:3], [l[:3] for l in levels_h], [o[:3] for o in outs_h], n_corr_h[:3])
+
+
+def test_mesh_renderer_extra_layers(dev, K):
+    """'depth' and 'camera_position' layers of the mesh renderer: with identity extrinsics camera == world position and
+    depth is its z; empty pixels (no mesh) are zero."""
+    from diffusionhandles_b200 import depth_transform as dt
+    from diffusionhandles_b200.renderer import Camera, MeshRenderer, SplatRendererArgs
+    S = 48
+    depth, bg, mask = O.synthetic_scene(S, 41)
+    fg_mesh = dt.depth_to_mesh(torch.from_numpy(depth).to(dev)[None, None], K, mask=torch.from_numpy(mask > 0.5).to(dev)[None, None])
+    r = MeshRenderer(['world_position', 'camera_position', 'depth'], SplatRendererArgs(device=dev, output_res=(S, S)))
+    r.update_scene({'meshes': [fg_mesh], 'cameras': [Camera(intrinsics=K)]})
+    out = r.render()
+    assert set(out) == {'world_position', 'camera_position', 'depth'}
+    assert torch.equal(out['world_position'], out['camera_position'])
+    d = out['depth']
+    assert d.shape[0] == 1 and d.shape[1] == S and d.shape[2] == S
+    assert torch.equal(d[0, ..., 0], out['world_position'][0, ..., 2])
+    covered = out['world_position'][0, ..., 3] > 0
+    assert 0 < int(covered.sum()) < S * S and float(out['world_position'][0][~covered].abs().max()) == 0.0
