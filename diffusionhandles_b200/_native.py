@@ -185,9 +185,14 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 def stream_handle(device: torch.device) -> int:
     """cudaStream_t of torch's current stream on ``device`` (the raw getter avoids building a Stream object per call)."""
+    cur = torch.cuda.current_device()
+    idx = cur if device.index is None else device.index
+    if idx != cur:
+        # the C ABI launches on the CURRENT device; a tensor that lives elsewhere would be dereferenced on the wrong GPU
+        raise NativeLibraryError(f"tensors are on cuda:{idx} but the current CUDA device is cuda:{cur}; "
+                                 f"run the call under `with torch.cuda.device({idx}):` (one process per GPU is the intended use)")
     if _raw_stream is not None:
-        idx = device.index
-        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -954,3 +954,19 @@ def test_mesh_renderer_extra_layers(dev, K):
     assert torch.equal(d[0, ..., 0], out['world_position'][0, ..., 2])
     covered = out['world_position'][0, ..., 3] > 0
     assert 0 < int(covered.sum()) < S * S and float(out['world_position'][0][~covered].abs().max()) == 0.0
+
+
+def test_device_mismatch_fails_loudly(dev, K):
+    """The C ABI launches on the current device: a tensor on another GPU must raise instead of being dereferenced on the
+    wrong one; under torch.cuda.device(...) the call works (needs two GPUs, otherwise skipped)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from diffusionhandles_b200 import depth_transform as dt, _native as N
+    other = torch.device("cuda", 1)
+    d = torch.rand(1, 1, 16, 16, device=other) + 1.0
+    with pytest.raises(N.NativeLibraryError):
+        dt.depth_to_world_coords(d, K)
+    with torch.cuda.device(other):
+        out = dt.depth_to_world_coords(d, K)
+    ref = dt.depth_to_world_coords(d.to(dev), K)
+    assert torch.equal(out.cpu(), ref.cpu())
