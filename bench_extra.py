@@ -59,9 +59,21 @@ def config1_and_5():
         for _ in range(20):
             eng.run(td, tb, tm, K, rg, poisson=False, sync_counts=True)
         wall = (time.perf_counter() - t0) / 20 * 1e3
+        extra = {}
+        if name == "config1":
+            # BASELINE config 1: "+ one 64x64x320 activation" warped through this edit (dense form through the winner map, and the
+            # list form A[:, y_src, x_src] that the reference's losses gather)
+            A = torch.randn((1, 320, 64, 64), generator=torch.Generator(device=dev).manual_seed(1), device=dev)
+            out = torch.empty_like(A)
+            maps = warp.dense_source_maps(res.corr, res.n_corr, S, [64], res.winner_src)
+            extra["gpu_ms_warp_320x64x64_dense"], _ = timeit(lambda: warp.warp_stacks([A], maps, [out]))
+            c = res.correspondences(0)
+            ys, xs = (c[:, 1] // (S // 64)), (c[:, 0] // (S // 64))
+            extra["gpu_ms_warp_320x64x64_list"], _ = timeit(lambda: warp.gather_list(A[0], ys, xs))
+            extra["gpu_ms_maps"], _ = timeit(lambda: warp.dense_source_maps(res.corr, res.n_corr, S, [64], res.winner_src))
         print(json.dumps({"config": name, "S": S, "n_fg": int(res.n_fg_host[0]), "n_corr": int(res.n_corr_host[0]),
                           "gpu_ms_geometry": med_np, "gpu_ms_with_poisson": med_p, "wall_ms_with_count_readback": wall,
-                          "poisson_iters": int(eng.poisson_iters[0].item())}), flush=True)
+                          "poisson_iters": int(eng.poisson_iters[0].item()), **extra}), flush=True)
         del eng
 
 
