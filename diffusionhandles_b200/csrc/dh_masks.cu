@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(256) dense_map_scatter_kernel(const int64_t* _
     if (n >= n_corr[e]) return;
     const int r = img_res / side;
     const longlong4 v = *reinterpret_cast<const longlong4*>(corr + ((size_t)e * corr_stride_rows + n) * 4);
+    if ((unsigned long long)v.x >= (unsigned long long)img_res || (unsigned long long)v.y >= (unsigned long long)img_res ||
+        (unsigned long long)v.z >= (unsigned long long)img_res || (unsigned long long)v.w >= (unsigned long long)img_res)
+        return;                                   // rows outside the image are ignored
     const int d = (int)(v.w / r) * side + (int)(v.z / r);
     atomicMin(src_map + (size_t)e * side * side + d, n);
 }
@@ -287,6 +290,10 @@ __global__ void __launch_bounds__(256) dense_maps_scatter_kernel(const int64_t* 
     const int n_e = n_corr[e];
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_e; n += gridDim.x * blockDim.x) {
         const longlong4 v = *reinterpret_cast<const longlong4*>(corr + ((size_t)e * corr_stride_rows + n) * 4);
+        // rows with a coordinate outside the image (never produced by dh_correspondences; a caller's own list might) are ignored
+        if ((unsigned long long)v.x >= (unsigned long long)lv.img_res || (unsigned long long)v.y >= (unsigned long long)lv.img_res ||
+            (unsigned long long)v.z >= (unsigned long long)lv.img_res || (unsigned long long)v.w >= (unsigned long long)lv.img_res)
+            continue;
 #pragma unroll
         for (int l = 0; l < kMaxMapLevels; ++l) {
             if (l >= lv.n_levels) break;

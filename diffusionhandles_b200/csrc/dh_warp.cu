@@ -160,10 +160,12 @@ __global__ void __launch_bounds__(kWarpThreads) warp_dense_tma_kernel(const __gr
             const int plane = el / hw;
             const int q0 = el - plane * hw;
             const int4 m = *reinterpret_cast<const int4*>(map + q0);
-            off[k][0] = m.x >= 0 ? plane * hw + m.x : -1;
-            off[k][1] = m.y >= 0 ? plane * hw + m.y : -1;
-            off[k][2] = m.z >= 0 ? plane * hw + m.z : -1;
-            off[k][3] = m.w >= 0 ? plane * hw + m.w : -1;
+            // (unsigned compare: negative = "no source", and an index >= hw from a caller's own map is treated the same way
+            // instead of reading outside the stage)
+            off[k][0] = (unsigned)m.x < (unsigned)hw ? plane * hw + m.x : -1;
+            off[k][1] = (unsigned)m.y < (unsigned)hw ? plane * hw + m.y : -1;
+            off[k][2] = (unsigned)m.z < (unsigned)hw ? plane * hw + m.z : -1;
+            off[k][3] = (unsigned)m.w < (unsigned)hw ? plane * hw + m.w : -1;
         }
         float* dst = L.out + (size_t)sg.edit * L.edit_floats;
         for (int c = sg.c0; c < sg.c1; ++c) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) gather_generic_kernel(const float* __rest
         const float* a = in + (size_t)c * hw_in;
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = id[j] >= 0 ? __ldg(a + id[j]) : 0.0f;
+        for (int j = 0; j < 4; ++j) v[j] = (unsigned)id[j] < (unsigned)hw_in ? __ldg(a + id[j]) : 0.0f;   // out of range -> 0, never a wild read
         float* o = out + (size_t)c * n + i0;
         if (vec) {
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);

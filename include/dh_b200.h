@@ -209,7 +209,9 @@ int dh_dense_source_maps(const int64_t* corr, const int32_t* n_corr, int corr_st
  * list form : out[c][n] = in[c][idx[n]]            (losses.py:46-47, :80)
  * dense form: out[c][q] = map[q] >= 0 ? in[c][map[q]] : 0, for every level of a stack, B edits.
  * The dense kernel stages 16 KB chunks of the source planes in shared memory with TMA bulk copies
- * (cp.async.bulk + mbarrier) and writes 128-bit rows. */
+ * (cp.async.bulk + mbarrier) and writes 128-bit rows.
+ * Indices outside [0, hw) - negative or too large - give 0 and are never dereferenced (the reference's tensor indexing
+ * would raise IndexError for them; a kernel cannot, so it stays memory safe instead). */
 int dh_warp_gather_list(const float* in, int C, int hw, const int32_t* idx, int n, float* out, void* stream);
 int dh_warp_gather_dense(const dh_warp_level* levels_host, int n_levels, int B, void* stream);
 

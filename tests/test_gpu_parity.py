@@ -970,3 +970,27 @@ def test_device_mismatch_fails_loudly(dev, K):
         out = dt.depth_to_world_coords(d, K)
     ref = dt.depth_to_world_coords(d.to(dev), K)
     assert torch.equal(out.cpu(), ref.cpu())
+
+
+def test_out_of_range_indices_are_memory_safe(dev):
+    """A caller's own maps / index lists may hold indices outside the plane: they give 0 (like 'no source') instead of a
+    wild read; rows of a correspondence list outside the image are ignored by the dense-map builder."""
+    from diffusionhandles_b200 import warp
+    A = torch.randn(2, 320, 64, 64, device=dev)
+    m = torch.randint(0, 4096, (2, 4096), device=dev, dtype=torch.int32)
+    m[0, 5], m[1, 77], m[1, 100] = 4096, 2 ** 30, -7
+    out = warp.warp_stacks([A], [m])[0]
+    valid = (m >= 0) & (m < 4096)
+    ref = torch.gather(A.flatten(2), 2, m.long().clamp(0, 4095)[:, None, :].expand(-1, 320, -1)) * valid[:, None, :]
+    assert torch.equal(out.flatten(2), ref)
+    B3 = torch.randn(3, 5, 7, 9, device=dev)                     # generic path
+    m3 = torch.randint(-2, 70, (3, 63), device=dev, dtype=torch.int32)
+    out3 = warp.warp_stacks([B3], [m3])[0]
+    v3 = (m3 >= 0) & (m3 < 63)
+    ref3 = torch.gather(B3.flatten(2), 2, m3.long().clamp(0, 62)[:, None, :].expand(-1, 5, -1)) * v3[:, None, :]
+    assert torch.equal(out3.flatten(2), ref3)
+    corr = torch.tensor([[[3, 4, 10, 12], [600, 4, 10, 12], [5, 5, -1, 3], [8, 9, 40, 511], [1, 1, 40, 512]]], dtype=torch.int64, device=dev)
+    n = torch.tensor([5], dtype=torch.int32, device=dev)
+    maps = warp.dense_source_maps(corr, n, 512, [64, 8])
+    m64 = maps[0][0].cpu().numpy()
+    assert (m64 >= 0).sum() == 2 and m64[(12 // 8) * 64 + 10 // 8] == (4 // 8) * 64 + 3 // 8 and m64[(511 // 8) * 64 + 40 // 8] == (9 // 8) * 64 + 8 // 8
