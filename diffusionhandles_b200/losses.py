@@ -20,6 +20,13 @@ _FG, _BG_GLOBAL, _BG_LOCAL = 1, 1, 2
 
 
 def _to_cells(y, x, grid: int, device) -> torch.Tensor:
+    """Cell ids y*grid + x on the device.  Host-side index arrays are range checked here (the reference's tensor indexing
+    raises IndexError for them; the kernels trust their lists); device tensors come from process_correspondences_device."""
+    for name, v in (("y", y), ("x", x)):
+        if not (isinstance(v, torch.Tensor) and v.is_cuda):
+            a = np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v)
+            if a.size and (a.min() < 0 or a.max() >= grid):
+                raise IndexError(f"{name} index out of range for a {grid} x {grid} loss grid: [{a.min()}, {a.max()}]")
     yy = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y).to(device=device, dtype=torch.int64)
     xx = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(device=device, dtype=torch.int64)
     return (yy.reshape(-1) * grid + xx.reshape(-1)).to(torch.int32).contiguous()

@@ -994,3 +994,14 @@ def test_out_of_range_indices_are_memory_safe(dev):
     maps = warp.dense_source_maps(corr, n, 512, [64, 8])
     m64 = maps[0][0].cpu().numpy()
     assert (m64 >= 0).sum() == 2 and m64[(12 // 8) * 64 + 10 // 8] == (4 // 8) * 64 + 3 // 8 and m64[(511 // 8) * 64 + 40 // 8] == (9 // 8) * 64 + 8 // 8
+
+
+def test_loss_index_lists_are_range_checked(dev):
+    from diffusionhandles_b200 import losses
+    f1, f2 = torch.randn(3, 64, 64, device=dev), torch.randn(3, 64, 64, device=dev, requires_grad=True)
+    ok = np.array([1, 2, 3])
+    with pytest.raises(IndexError):
+        losses.local_average_feat_l1_loss(f1, f2, np.array([1, 64, 3]), ok, ok, ok)
+    with pytest.raises(IndexError):
+        losses.average_feat_l1_loss(f1, f2, ok, ok, ok, np.array([-1, 2, 3]))
+    assert torch.isfinite(losses.local_average_feat_l1_loss(f1, f2, ok, ok, ok, ok))
