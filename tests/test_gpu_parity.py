@@ -1005,3 +1005,21 @@ def test_loss_index_lists_are_range_checked(dev):
     with pytest.raises(IndexError):
         losses.average_feat_l1_loss(f1, f2, ok, ok, ok, np.array([-1, 2, 3]))
     assert torch.isfinite(losses.local_average_feat_l1_loss(f1, f2, ok, ok, ok, ok))
+
+
+def test_poisson_solve_large_system_uses_the_global_path(dev):
+    """More than 32k unknowns: the solver's L2-resident path (the shared-memory path takes the smaller systems); an
+    irregular hole of ~45k pixels against SuperLU."""
+    from diffusionhandles_b200 import depth_transform as dt
+    S = 384
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:S, 0:S]
+    img = (50 + 30 * np.sin(xx / 37.0) + 0.2 * yy + rng.normal(size=(S, S))).astype(np.float32)
+    mask = ((xx - 190) ** 2 / 150.0 ** 2 + (yy - 200) ** 2 / 100.0 ** 2) < 1.0
+    mask &= ~(((xx - 150) ** 2 + (yy - 180) ** 2) < 20 ** 2)            # an island of known pixels inside the hole
+    mask[:, :3] = False
+    assert mask.sum() > 8 * 4096
+    out = dt.poisson_solve(img, mask)                                   # NumPy in / NumPy out like the reference
+    ref = O.poisson_solve(img, mask)
+    assert np.array_equal(out[~mask], img[~mask])
+    assert np.abs(out - ref).max() <= 1e-3
