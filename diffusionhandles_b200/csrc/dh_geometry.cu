@@ -170,45 +170,61 @@ __global__ void __launch_bounds__(kTileThreads) fg_compact_kernel(
 }
 
 // Sequential fp32 sum in raster order, one warp per component (np.mean(points[mask], axis=0) adds row
-// by row, depth_transform.py:509).  All 32 lanes carry the same running sum; the addends are fetched
-// 256 at a time (two coalesced float4 per lane, next tile prefetched while the current one is consumed)
-// and broadcast with shuffles, so only the dependent FADD chain (4 cycles per element) is serial.
+// by row, depth_transform.py:509).  All 32 lanes carry the same running sum.  The addends are staged in
+// shared memory 512 at a time with asynchronous copies (a ring of tiles per warp) and read back with 128-bit
+// broadcast loads into a REGISTER double buffer of 32 values: while the dependent FADD chain (4 cycles per
+// element) works through one group, the loads of the next group are already in flight.
 __global__ void __launch_bounds__(96) fg_centroid_kernel(const float* __restrict__ fgX, const float* __restrict__ fgY,
                                                          const float* __restrict__ fgZ, const int32_t* __restrict__ n_fg,
                                                          int P, float* __restrict__ centroid) {
+    constexpr int kTileF = 512, kBuf = 4, kGroup = 8;            // floats per tile, ring depth, float4 per register group
+    __shared__ __align__(16) float ring[3][kBuf][kTileF];
     const int e = blockIdx.x, comp = warp_id(), lane = lane_id();
     const float* a = (comp == 0 ? fgX : comp == 1 ? fgY : fgZ) + (size_t)e * P;   // 256-byte aligned (workspace layout)
     const int n = n_fg[e];
     const unsigned full = 0xFFFFFFFFu;
     float s = 0.0f;
-    const int n_tiles = (reinterpret_cast<uintptr_t>(a) & 15) == 0 ? n / 256 : 0;
-    float4 nx0 = make_float4(0, 0, 0, 0), nx1 = nx0;
-    if (n_tiles > 0) {
-        nx0 = *reinterpret_cast<const float4*>(a + lane * 4);
-        nx1 = *reinterpret_cast<const float4*>(a + 128 + lane * 4);
-    }
+    const int n_tiles = (reinterpret_cast<uintptr_t>(a) & 15) == 0 ? n / kTileF : 0;
+    auto issue = [&](int t) {
+        if (t < n_tiles) {
+            const float* src = a + (size_t)t * kTileF + lane * 4;
+            float* dst = &ring[comp][t % kBuf][lane * 4];
+#pragma unroll
+            for (int q = 0; q < kTileF / 128; ++q)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 128 * q)),
+                             "l"(src + 128 * q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");       // (empty groups keep the wait count uniform)
+    };
+#pragma unroll
+    for (int t = 0; t < kBuf - 1; ++t) issue(t);
     for (int t = 0; t < n_tiles; ++t) {
-        const float4 v0 = nx0, v1 = nx1;
-        if (t + 1 < n_tiles) {
-            nx0 = *reinterpret_cast<const float4*>(a + (size_t)(t + 1) * 256 + lane * 4);
-            nx1 = *reinterpret_cast<const float4*>(a + (size_t)(t + 1) * 256 + 128 + lane * 4);
-        }
+        issue(t + kBuf - 1);                                        // refills the slot consumed in iteration t - 1
+        asm volatile("cp.async.wait_group %0;" ::"n"(kBuf - 1) : "memory");
+        __syncwarp();
+        const float4* tile = reinterpret_cast<const float4*>(ring[comp][t % kBuf]);
+        float4 cur[kGroup], nxt[kGroup];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            s = __fadd_rn(s, __shfl_sync(full, v0.x, j));
-            s = __fadd_rn(s, __shfl_sync(full, v0.y, j));
-            s = __fadd_rn(s, __shfl_sync(full, v0.z, j));
-            s = __fadd_rn(s, __shfl_sync(full, v0.w, j));
-        }
+        for (int j = 0; j < kGroup; ++j) cur[j] = tile[j];          // same address in every lane: broadcast
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            s = __fadd_rn(s, __shfl_sync(full, v1.x, j));
-            s = __fadd_rn(s, __shfl_sync(full, v1.y, j));
-            s = __fadd_rn(s, __shfl_sync(full, v1.z, j));
-            s = __fadd_rn(s, __shfl_sync(full, v1.w, j));
+        for (int g = 0; g < kTileF / 4 / kGroup; ++g) {
+            if (g + 1 < kTileF / 4 / kGroup) {
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) nxt[j] = tile[(g + 1) * kGroup + j];
+            }
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                s = __fadd_rn(s, cur[j].x);
+                s = __fadd_rn(s, cur[j].y);
+                s = __fadd_rn(s, cur[j].z);
+                s = __fadd_rn(s, cur[j].w);
+            }
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) cur[j] = nxt[j];
         }
+        __syncwarp();                                               // every lane is done with the slot before it is refilled
     }
-    for (int base = n_tiles * 256; base < n; base += 32) {
+    for (int base = n_tiles * kTileF; base < n; base += 32) {
         const float v = base + lane < n ? a[base + lane] : 0.0f;
         const int cnt = min(32, n - base);
         for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(full, v, j));
