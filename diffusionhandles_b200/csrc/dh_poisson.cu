@@ -26,15 +26,30 @@ constexpr int kPoissonCluster = 8;
 // distributed shared memory.  Larger systems use the global-memory (L2) path.
 constexpr int kSmemUnknowns = 4096;
 constexpr size_t kPoissonSmemBytes = (size_t)kSmemUnknowns * (5 * sizeof(double) + 4 * sizeof(uint32_t));
-constexpr uint32_t kNoNbr = 0xFFFFFFFFu;
 
 __device__ __forceinline__ bool bit_at(const uint32_t* bits, int wpr, int row, int col) {
     return (bits[row * wpr + (col >> 5)] >> (col & 31)) & 1u;
 }
 
+__device__ __forceinline__ uint32_t cluster_addr(const void* smem_ptr, int rank) {      // shared::cluster address of a CTA's smem
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double ld_cluster_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cluster_f64x2(uint32_t addr, double a, double b) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+
 // Two sums over the whole cluster in one reduction (one cluster barrier), identical in every thread of every CTA.
+// All-to-all: every CTA pushes its pair of partials into the slot array of EVERY CTA before the barrier (remote stores are
+// fire and forget), so that after the barrier each CTA sums eight LOCAL entries in rank order.
 __device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double& a, double& b, double (*warp_sm2)[2],
-                                             double (*part_sm2)[2], int slot) {
+                                             double (*part_all)[kPoissonCluster][2], int slot) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
@@ -49,15 +64,13 @@ __device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double&
             ta += __shfl_xor_sync(0xFFFFFFFFu, ta, o);
             tb += __shfl_xor_sync(0xFFFFFFFFu, tb, o);
         }
-        if (lane_id() == 0) { part_sm2[slot][0] = ta; part_sm2[slot][1] = tb; }
+        if (lane_id() < kPoissonCluster)
+            st_cluster_f64x2(cluster_addr(&part_all[slot][cluster.block_rank()][0], lane_id()), ta, tb);
     }
     cluster.sync();
     a = 0.0; b = 0.0;
 #pragma unroll
-    for (int r = 0; r < kPoissonCluster; ++r) {
-        const double* q = &cluster.map_shared_rank(&part_sm2[0][0], r)[2 * slot];
-        a += q[0]; b += q[1];
-    }
+    for (int r = 0; r < kPoissonCluster; ++r) { a += part_all[slot][r][0]; b += part_all[slot][r][1]; }
 }
 
 // Sum over the whole cluster, identical in every thread of every CTA.  `slot` alternates between calls so that one
@@ -90,7 +103,7 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
     __shared__ double warp_sm[32];
     __shared__ double part_sm[4];
     __shared__ double warp_sm2[32][2];
-    __shared__ double part_sm2[2][2];
+    __shared__ __align__(16) double part_sm2[2][kPoissonCluster][2];
     __shared__ int scan_smem[33];
     __shared__ int count_sm;
     const int e = blockIdx.y, tid = threadIdx.x, P = H * W, nwords = H * wpr;
@@ -154,17 +167,22 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
         uint32_t* const nb_s = reinterpret_cast<uint32_t*>(wv + kSmemUnknowns);     // [4][kSmemUnknowns]: rank << 16 | local index
         const int m_own = (n + kPoissonCluster - 1) / kPoissonCluster;              // unknowns per CTA (contiguous, raster order)
         const int k0 = min(n, rank * m_own), k1 = min(n, k0 + m_own), mine = k1 - k0;
-        auto compact_of = [&](int row, int col) -> uint32_t {                       // packed owner / local index of an unknown pixel
+        __shared__ double zero_sm;
+        if (tid == 0) zero_sm = 0.0;
+        const uint32_t zero_addr = cluster_addr(&zero_sm, rank);
+        // shared::cluster address of the residual of an unknown pixel (in whichever CTA owns it): one load per neighbour
+        // in the iteration, no owner test, no pointer arithmetic
+        auto compact_of = [&](int row, int col) -> uint32_t {
             const int w = row * wpr + (col >> 5);
             const int k = word_prefix[w] + __popc(mask[w] & ((1u << (col & 31)) - 1u));
             const int rk = k / m_own;
-            return ((uint32_t)rk << 16) | (uint32_t)(k - rk * m_own);
+            return cluster_addr(rs + (k - rk * m_own), rk);
         };
         double bb_part = 0.0;
         for (int j = tid; j < mine; j += kPoissonThreads) {
             const int q = list[k0 + j], row = q / W, col = q - row * W;
             double b = 0.0;
-            uint32_t nb4[4] = {kNoNbr, kNoNbr, kNoNbr, kNoNbr};
+            uint32_t nb4[4] = {zero_addr, zero_addr, zero_addr, zero_addr};   // absent / known neighbours read a local zero
             if (row > 0) { if (bit_at(mask, wpr, row - 1, col)) nb4[0] = compact_of(row - 1, col); else b += (double)img[q - W]; }
             if (row < H - 1) { if (bit_at(mask, wpr, row + 1, col)) nb4[1] = compact_of(row + 1, col); else b += (double)img[q + W]; }
             if (col > 0) { if (bit_at(mask, wpr, row, col - 1)) nb4[2] = compact_of(row, col - 1); else b += (double)img[q - 1]; }
@@ -186,19 +204,12 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
         double rr0 = cluster_sum(cluster, bb_part, warp_sm, part_sm, 0);    // (its barrier also publishes the residuals)
         const double stop = rel_tol * rel_tol * rr0;
         if (max_iter <= 0) max_iter = 20000;
-        auto res_at = [&](uint32_t packed) -> double {
-            const int rk = (int)(packed >> 16), loc = (int)(packed & 0xFFFFu);
-            return rk == rank ? rs[loc] : cluster.map_shared_rank(rs, rk)[loc];
-        };
         auto spmv_dots = [&](double& g_part, double& d_part) {
             for (int j = tid; j < mine; j += kPoissonThreads) {
                 const double rq = rs[j];
-                double a = 4.0 * rq;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const uint32_t nb = nb_s[d * kSmemUnknowns + j];
-                    if (nb != kNoNbr) a -= res_at(nb);
-                }
+                const double n0 = ld_cluster_f64(nb_s[j]), n1 = ld_cluster_f64(nb_s[kSmemUnknowns + j]);
+                const double n2 = ld_cluster_f64(nb_s[2 * kSmemUnknowns + j]), n3 = ld_cluster_f64(nb_s[3 * kSmemUnknowns + j]);
+                const double a = 4.0 * rq - n0 - n1 - n2 - n3;
                 wv[j] = a;
                 g_part += rq * rq;
                 d_part += a * rq;
