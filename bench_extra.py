@@ -131,7 +131,6 @@ def config3():
 
 def config4():
     import bench
-    from diffusionhandles_b200 import _native
     scenes, edits = bench.edit_recipe(256)
     K = GuidedStableDiffuser.get_depth_intrinsics()
     sc = [synthetic_scene(**s) for s in scenes]

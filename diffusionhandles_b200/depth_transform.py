@@ -14,7 +14,7 @@ import torch
 
 from . import _native as N
 from .engine import get_engine, make_rigid, pixel_grid
-from .utils import pack_correspondences
+from .utils import pack_correspondences  # noqa: F401  (re-exported: the reference's depth_transform imports it too)
 
 
 def normalize_depth(depth, bounds=None, return_bounds=False):
