@@ -934,8 +934,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         // The two kernels are independent (they only meet in loss_finish through an atomic ticket), so the second one is
         // a programmatic dependent launch: its CTAs become resident as the first kernel's CTAs retire instead of waiting
         // for the whole grid, which hides the launch gap and the tail of the first kernel.
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid_f); cfg.blockDim = dim3(kLossThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
