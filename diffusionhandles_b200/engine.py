@@ -147,6 +147,9 @@ class EditEngine:
         self.poisson_ws_bytes = int(self.lib.dh_poisson_workspace_bytes(B, H, W))
         self.poisson_ws = torch.empty(self.poisson_ws_bytes, dtype=u8, device=dev)
         self.poisson_iters = torch.zeros((B,), dtype=i32, device=dev)
+        # relative residual at which the CG hole fill stops (fp64).  The filled disparity is cast to fp32: from 1e-9 downwards the
+        # result does not change any more (tools/poisson_tolerance.py), 1e-11 keeps two orders of margin for ill-conditioned holes
+        self.poisson_rel_tol = 1e-11
         self.n_pinned = torch.empty((2, B), dtype=i32).pin_memory()
         self.xs, self.ys = pixel_grid(H, W, dev)
         S = max(H, W)
@@ -193,7 +196,7 @@ class EditEngine:
         disparity = None
         if poisson:
             N.check(lib.dh_poisson_fill(N.ptr(self.disparity_raw), N.ptr(self.cleaned_bits), N.ptr(self.target_bits), B, H, W,
-                                        N.ptr(self.disparity), 0, 1e-13, N.ptr(self.poisson_iters),
+                                        N.ptr(self.disparity), 0, self.poisson_rel_tol, N.ptr(self.poisson_iters),
                                         N.ptr(self.poisson_ws), self.poisson_ws_bytes, st), "dh_poisson_fill")
             disparity = self.disparity
         res = EditResult(B=B, H=H, W=W, n_fg=self.n_fg, n_corr=self.n_corr, centroid=self.centroid, pix=self.pix,
