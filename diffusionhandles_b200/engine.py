@@ -148,7 +148,7 @@ class EditEngine:
         self.poisson_ws = torch.empty(self.poisson_ws_bytes, dtype=u8, device=dev)
         self.poisson_iters = torch.zeros((B,), dtype=i32, device=dev)
         # relative residual at which the CG hole fill stops (fp64).  The filled disparity is cast to fp32: from 1e-9 downwards the
-        # result does not change any more (tools/poisson_tolerance.py), 1e-11 keeps two orders of margin for ill-conditioned holes
+        # result does not change any more (tests/fuzz/poisson_tolerance.py), 1e-11 keeps two orders of margin for ill-conditioned holes
         self.poisson_rel_tol = 1e-11
         self.n_pinned = torch.empty((2, B), dtype=i32).pin_memory()
         self.xs, self.ys = pixel_grid(H, W, dev)

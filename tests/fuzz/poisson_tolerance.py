@@ -1,12 +1,12 @@
+"""Sweep of the hole-fill stopping tolerance against the SuperLU result (test tooling: uses the oracle)."""
 import os, sys, numpy as np, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests/fuzz")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE))); sys.path.insert(0, HERE)
 from oracle import dh_oracle as O
 import fuzz_more as F
 from diffusionhandles_b200 import engine as E
 from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
 dev = torch.device("cuda:0"); K = GuidedStableDiffuser.get_depth_intrinsics(); K_NP = K.numpy()
-import diffusionhandles_b200.engine as eng_mod
-src = open(eng_mod.__file__).read()
 rng = np.random.default_rng(3)
 cases = []
 for _ in range(40):
@@ -17,7 +17,7 @@ for tol in (1e-13, 1e-11, 1e-10, 1e-9):
     errs, its = [], []
     for S, d, b, m, a, ax, t in cases:
         o = O.transform_depth_pc(d, b, m, K_NP, a, ax, tuple(float(np.float32(v)) for v in t), poisson=True)
-        e = E.get_engine(dev, 1, S, S)
+        e = E.EditEngine(dev, 1, S, S)  # private engine: the cached one keeps its tolerance
         td, tb, tm = (torch.from_numpy(x).to(dev)[None].contiguous() for x in (d, b, m))
         e.poisson_rel_tol = tol
         res = e.run(td, tb, tm, K, [E.make_rigid(a, list(ax), list(t))], poisson=True)
