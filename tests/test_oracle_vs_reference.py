@@ -13,7 +13,9 @@ from helpers import f32_translation
 pytestmark = [pytest.mark.reference,
               pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")]
 
-SCENES = [("sunflower", "edit_000"), ("car", "edit_002"), ("shoe", "edit_000"), ("chair_2", "edit_000")]
+def _scenes():
+    root = os.path.join(REFERENCE_ROOT, "test", "data", "photogen")
+    return sorted(d for d in os.listdir(root) if os.path.isdir(os.path.join(root, d))) if os.path.isdir(root) else []
 
 
 @pytest.fixture(scope="module")
@@ -35,19 +37,26 @@ def load_scene(name):
     return depth, bg, mask, tr
 
 
-@pytest.mark.parametrize("scene,edit", SCENES)
-def test_bundled_scene(ref, scene, edit):
+@pytest.mark.parametrize("scene", _scenes())
+def test_bundled_scene(ref, scene):
+    """LIVE: all 20 bundled scenes x all their edits (90), the way the reference's test driver runs them
+    (test/test_diffusion_handles.py:117, :145): set_foreground's solve_laplacian_depth, then transform_depth_pc."""
+    import scipy.ndimage
     import torch
     depth, bg, mask, tr = load_scene(scene)
-    t = tr[edit]
     K = ref.get_depth_intrinsics()
-    disp, corr = ref.depth_transform.transform_depth_pc(
-        torch.from_numpy(depth)[None, None], torch.from_numpy(bg)[None, None], torch.from_numpy(mask)[None, None], K,
-        rot_angle=t["rotation_angle"], rot_axis=torch.tensor(t["rotation_axis"], dtype=torch.float32),
-        translation=torch.tensor(t["translation"], dtype=torch.float32))
-    o = O.transform_depth_pc(depth, bg, mask, K.numpy(), t["rotation_angle"], t["rotation_axis"], f32_translation(t["translation"]))
-    assert np.array_equal(corr.numpy(), o["correspondences"])
-    assert np.array_equal(disp[0, 0].numpy(), o["disparity"])
+    dil = scipy.ndimage.binary_dilation(mask, iterations=15)
+    bg_ref = ref.utils.solve_laplacian_depth(depth, bg, dil)
+    bg2 = O.solve_laplacian_depth(depth, bg, dil)
+    assert bg2.dtype == bg_ref.dtype and np.array_equal(bg2, bg_ref)
+    for edit, t in tr.items():
+        disp, corr = ref.depth_transform.transform_depth_pc(
+            torch.from_numpy(depth)[None, None], torch.from_numpy(bg_ref)[None, None], torch.from_numpy(mask)[None, None], K,
+            rot_angle=t["rotation_angle"], rot_axis=torch.tensor(t["rotation_axis"], dtype=torch.float32),
+            translation=torch.tensor(t["translation"], dtype=torch.float32))
+        o = O.transform_depth_pc(depth, bg2, mask, K.numpy(), t["rotation_angle"], t["rotation_axis"], f32_translation(t["translation"]))
+        assert np.array_equal(corr.numpy(), o["correspondences"]), edit
+        assert np.array_equal(disp[0, 0].numpy(), o["disparity"]), edit
 
 
 def test_general_axis_is_within_contract(ref):
