@@ -5,23 +5,30 @@
 //
 // (1) dh_build_loss_plan - once per edit.  The correspondence list has ~6x duplicates at the 64x64 loss grid
 //     (SURVEY.md "hard parts"); the plan groups it by DESTINATION cell (counting sort) and collapses equal
-//     (src, dst) cell pairs into one entry with a multiplicity, giving a CSR over destination cells
-//     (row_ptr, 8-byte pairs: src | dst << 16, multiplicity) plus per-cell multiplicities of the three background lists.
+//     (src, dst) cell pairs into one entry with a multiplicity: a CSR over destination cells (row_ptr, 8-byte pairs)
+//     for the general patch kernel, a sliced-ELL view of the same pairs for this file's kernel (dh_loss_plan.cuh),
+//     plus per-cell multiplicities of the three background lists.
 //
-// (2) dh_guidance_loss - every denoising step.  Two kernels of small persistent CTAs (256 threads, three per SM) pull
-//     (layer, channel) planes from a dynamic queue and evaluate, per plane,
+// (2) dh_guidance_loss - every denoising step.  ONE persistent launch for every layer: small CTAs (256 threads, four per
+//     SM) pull work items - one 64x64 plane pair, or a few planes of a smaller layer - from a dynamic queue.  The item's
+//     `cur` and `orig` planes are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that
+//     thread 0 issues for the NEXT item as soon as every warp is done reading the current one, so the HBM reads overlap
+//     the gradient write-out of this CTA and the arithmetic of the other CTAs of the SM.
+//     Per plane
 //         L_fg  = 1/(C N)  sum_pairs mult * |up(orig)[src] - up(cur)[dst]|
 //         dL/dup(cur)[dst] = -1/(C N) sum_pairs mult * sign(...)
-//     plus the background term.  The sign terms are accumulated as INTEGERS per destination cell (shared-memory
-//     atomics): integer addition is associative, so the gradient is bit-reproducible (the reference's
-//     index_put(accumulate=True) backward is not, on CUDA).  Layers smaller than the loss grid are resized
-//     bilinearly inside the box of pair cells only, and their gradient is written at native resolution through
-//     the transposed resize in gather form.  Loss value and gradient come out of the same pass: algorithmic
-//     traffic = read cur + read orig + write grad.  The last CTA to finish reduces the per-channel partial sums in
-//     a fixed order; the second kernel is a programmatic dependent launch so that it fills the SMs as the first drains.
+//     plus the background term.  One THREAD owns one destination cell (sliced ELL): it reads cur[dst] once, walks the
+//     cell's distinct sources and keeps the INTEGER sign count in a register - no atomics, and integer addition is
+//     associative, so the gradient is bit-reproducible (the reference's index_put(accumulate=True) backward is not, on
+//     CUDA).  Layers smaller than the loss grid are resized bilinearly inside the box of pair cells only, and their
+//     gradient is written at native resolution through the transposed resize in gather form.  Loss value and gradient
+//     come out of the same pass: algorithmic traffic = read cur + read orig + write grad.  The last CTA to finish reduces
+//     the per-channel partial sums in a fixed order and re-zeroes the two queue counters for the next launch.
 #include "dh_common.cuh"
 #include "dh_loss_plan.cuh"
+#include "dh_tma.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace dh {
@@ -30,7 +37,9 @@ namespace dh {
 // plan builder: one CTA of 1024 threads
 // ------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 1024;
-constexpr int kPlanCountWarps = 8;
+constexpr int kPlanWarps = kPlanThreads / 32;
+constexpr int kPlanTab = 1024;          // per-warp counter table: source cells lo .. lo + 1023 of one destination bucket per pass
+constexpr int kLenClasses = 256;        // rows are ordered by min(length, 255), descending
 
 __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     const int32_t* __restrict__ fg_src, const int32_t* __restrict__ fg_dst, int n_fg,
@@ -42,7 +51,9 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     int* hist = psm;                       // cells
     int* start = psm + cells;              // cells + 1
     int* ucount = start + cells + 1;       // cells
-    uint32_t* counters = reinterpret_cast<uint32_t*>(ucount + cells);   // kPlanCountWarps * cells
+    uint32_t* tabs = reinterpret_cast<uint32_t*>(ucount + cells);   // kPlanWarps * kPlanTab
+    int32_t* bucket = scratch;             // n_fg: sources grouped by destination cell
+    int32_t* uniq = scratch + n_fg;        // n_fg: per bucket, distinct sources (ascending) | multiplicity << 16
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     PlanView pv = plan_view(plan, grid, n_fg);
 
@@ -62,58 +73,159 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     __syncthreads();
     for (int i = tid; i < cells; i += kPlanThreads) hist[i] = start[i];        // cursors
     __syncthreads();
-    for (int n = tid; n < n_fg; n += kPlanThreads) scratch[atomicAdd(hist + fg_dst[n], 1)] = fg_src[n];
+    for (int n = tid; n < n_fg; n += kPlanThreads) bucket[atomicAdd(hist + fg_dst[n], 1)] = fg_src[n];
     __syncthreads();
-    // per destination cell: count the sources (shared-memory counters, one private table per warp), then emit the
-    // distinct sources in ascending order in place of the bucket
-    if (wid < kPlanCountWarps) {
-        uint32_t* cnt = counters + (size_t)wid * cells;
-        for (int d = wid; d < cells; d += kPlanCountWarps) {
+    // per destination cell (one warp each, all 32 warps): count the sources in a private shared-memory table that covers
+    // kPlanTab consecutive source cells per pass (one pass for any rigid edit: a bucket's sources span a few grid rows),
+    // then emit the distinct sources in ascending order
+    {
+        uint32_t* cnt = tabs + (size_t)wid * kPlanTab;
+        for (int d = wid; d < cells; d += kPlanWarps) {
             const int b0 = start[d], b1 = start[d + 1];
             if (b0 == b1) continue;
             int lo = 0x7FFFFFFF, hi = -1;
-            for (int k = b0 + lane; k < b1; k += 32) { const int v = scratch[k]; lo = min(lo, v); hi = max(hi, v); }
+            for (int k = b0 + lane; k < b1; k += 32) { const int v = bucket[k]; lo = min(lo, v); hi = max(hi, v); }
             lo = __reduce_min_sync(0xFFFFFFFFu, lo);
             hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-            for (int i = lo + lane; i <= hi; i += 32) cnt[i] = 0;
-            __syncwarp();
-            for (int k = b0 + lane; k < b1; k += 32) atomicAdd(cnt + scratch[k], 1u);
-            __syncwarp();
             int out = b0;
-            for (int base = lo; base <= hi; base += 32) {
-                const int i = base + lane;
-                uint32_t c = i <= hi ? cnt[i] : 0u;
-                while (__any_sync(0xFFFFFFFFu, c > 0)) {
-                    const unsigned b = __ballot_sync(0xFFFFFFFFu, c > 0);
-                    const uint32_t m = c > 65535u ? 65535u : c;
-                    if (c > 0) scratch[out + __popc(b & ((1u << lane) - 1u))] = (int32_t)((uint32_t)i | (m << 16));
-                    c -= m;
-                    out += __popc(b);
+            for (int w0 = lo; w0 <= hi; w0 += kPlanTab) {
+                const int w1 = min(hi, w0 + kPlanTab - 1);
+                for (int i = lane; i <= w1 - w0; i += 32) cnt[i] = 0;
+                __syncwarp();
+                for (int k = b0 + lane; k < b1; k += 32) {
+                    const int v = bucket[k];
+                    if (v >= w0 && v <= w1) atomicAdd(cnt + (v - w0), 1u);
                 }
+                __syncwarp();
+                for (int base = w0; base <= w1; base += 32) {
+                    const int i = base + lane;
+                    uint32_t c = i <= w1 ? cnt[i - w0] : 0u;
+                    while (__any_sync(0xFFFFFFFFu, c > 0)) {
+                        const unsigned b = __ballot_sync(0xFFFFFFFFu, c > 0);
+                        const uint32_t m = c > 65535u ? 65535u : c;
+                        if (c > 0) uniq[out + __popc(b & ((1u << lane) - 1u))] = (int32_t)((uint32_t)i | (m << 16));
+                        c -= m;
+                        out += __popc(b);
+                    }
+                }
+                __syncwarp();
             }
             if (lane == 0) ucount[d] = out - b0;
-            __syncwarp();
         }
     }
     __syncthreads();
-    // row_ptr = exclusive scan of the distinct-pair counts, then compact the buckets
+    // row_ptr = exclusive scan of the distinct-pair counts, then compact the buckets into the CSR
     s = 0;
     for (int i = c0; i < c1; ++i) s += ucount[i];
     run = block_exclusive_scan(s, scan_smem, total);
+    const int n_pairs = total;
     for (int i = c0; i < c1; ++i) {
         pv.row_ptr[i] = run;
         const int b0 = start[i];
         for (int j = 0; j < ucount[i]; ++j) {
-            const uint32_t e = (uint32_t)scratch[b0 + j];
+            const uint32_t e = (uint32_t)uniq[b0 + j];
             pv.pairs[run + j] = make_uint2((e & 0xFFFFu) | ((uint32_t)i << 16), e >> 16);
         }
         run += ucount[i];
     }
+    if (tid == 0) pv.row_ptr[cells] = n_pairs;
+    __syncthreads();
+
+    // ---- sliced-ELL view: rows (destination cells with pairs) in descending order of their length, ties in raster order ----
+    int* whist = reinterpret_cast<int*>(tabs);                       // [kPlanWarps][kLenClasses] per-warp class histograms
+    int* wbase = whist + kPlanWarps * kLenClasses;                    // same shape: running output positions
+    int* order = hist;                                                // row -> destination cell
+    int* soff = start;                                                // slice -> first entry group
+    for (int i = tid; i < kPlanWarps * kLenClasses; i += kPlanThreads) whist[i] = 0;
+    __syncthreads();
+    const int cpw = (cells + kPlanWarps - 1) / kPlanWarps;            // contiguous cells per warp
+    for (int i = lane; i < cpw; i += 32) {
+        const int cell = wid * cpw + i;
+        const int k = cell < cells ? min(ucount[cell], kLenClasses - 1) : 0;
+        if (k > 0) atomicAdd(whist + wid * kLenClasses + k, 1);
+    }
+    __syncthreads();
+    {   // exclusive scan in (class descending, warp ascending) order; element j = (255 - class) * 32 + warp
+        constexpr int kPer = kPlanWarps * kLenClasses / kPlanThreads;        // 8
+        int cs[kPer];
+        s = 0;
+#pragma unroll
+        for (int t = 0; t < kPer; ++t) {
+            const int j = tid * kPer + t, k = kLenClasses - 1 - (j / kPlanWarps), w = j % kPlanWarps;
+            cs[t] = k > 0 ? whist[w * kLenClasses + k] : 0;
+            s += cs[t];
+        }
+        run = block_exclusive_scan(s, scan_smem, total);
+#pragma unroll
+        for (int t = 0; t < kPer; ++t) {
+            const int j = tid * kPer + t, k = kLenClasses - 1 - (j / kPlanWarps), w = j % kPlanWarps;
+            wbase[w * kLenClasses + k] = run;
+            run += cs[t];
+        }
+    }
+    const int n_rows = total;
+    const int n_slices = (n_rows + 31) / 32;
+    __syncthreads();
+    for (int i0 = 0; i0 < cpw; i0 += 32) {      // stable placement: cells of a warp in ascending order, 32 at a time
+        const int cell = wid * cpw + i0 + lane;
+        const int k = (i0 + lane < cpw && cell < cells) ? min(ucount[cell], kLenClasses - 1) : 0;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, k);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (k > 0) order[wbase[wid * kLenClasses + k] + rank] = cell;
+        __syncwarp();
+        if (k > 0 && rank == 0) wbase[wid * kLenClasses + k] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // slice widths (longest row of the slice) and their exclusive scan
+        int w = 0;
+        if (tid < n_slices)
+            for (int r = tid * 32; r < min(n_rows, tid * 32 + 32); ++r) w = max(w, ucount[order[r]]);
+        run = block_exclusive_scan(w, scan_smem, total);
+        if (tid < n_slices) { soff[tid] = run; pv.ell_off[tid] = run; }
+        if (tid == 0) { soff[n_slices] = total; pv.ell_off[n_slices] = total; }
+    }
+    const int n_groups = total;
+    __syncthreads();
+    // box of the cells that are the source or the destination of a pair (resized layers work inside it)
+    __shared__ int box_sm[4];
+    __shared__ int nonbin_sm;
+    int* is_src = reinterpret_cast<int*>(tabs) + 2 * kPlanWarps * kLenClasses;     // cells ints behind the ELL histograms
+    for (int i = tid; i < cells; i += kPlanThreads) is_src[i] = 0;
+    if (tid == 0) { box_sm[0] = grid; box_sm[1] = -1; box_sm[2] = grid; box_sm[3] = -1; nonbin_sm = 0; }
+    __syncthreads();
+    for (int n = tid; n < n_fg; n += kPlanThreads) is_src[fg_src[n]] = 1;
+    __syncthreads();
+    for (int i = tid; i < cells; i += kPlanThreads)
+        if (is_src[i] || ucount[i] > 0) {
+            const int r = i / grid, c = i - r * grid;
+            atomicMin(box_sm + 0, r); atomicMax(box_sm + 1, r); atomicMin(box_sm + 2, c); atomicMax(box_sm + 3, c);
+        }
+    __syncthreads();
+    const int box_r0 = box_sm[0], box_r1 = box_sm[1], box_s0 = box_sm[2], box_s1 = box_sm[3];
+    const int box_w = box_s1 >= box_s0 ? box_s1 - box_s0 + 1 : 0;
+    auto to_box = [&](int cell) { const int r = cell / grid; return (r - box_r0) * box_w + (cell - r * grid - box_s0); };
+    for (int sl = wid; sl < n_slices; sl += kPlanWarps) {
+        const int r = sl * 32 + lane;
+        const int cell = r < n_rows ? order[r] : -1;
+        const int len = cell >= 0 ? ucount[cell] : 0;
+        const int base = cell >= 0 ? pv.row_ptr[cell] : 0;
+        pv.row_desc[r] = cell >= 0 ? ((uint32_t)cell | ((uint32_t)len << 16)) : 0u;
+        pv.row_desc_box[r] = cell >= 0 ? ((uint32_t)to_box(cell) | ((uint32_t)len << 16)) : 0u;
+        uint32_t* dst = pv.ent + (size_t)soff[sl] * 32 + lane;
+        uint32_t* dst_box = pv.ent_box + (size_t)soff[sl] * 32 + lane;
+        for (int k = 0; k < len; ++k) {
+            const uint2 e = pv.pairs[base + k];
+            dst[(size_t)k * 32] = (e.x & 0xFFFFu) | (e.y << 12);
+            dst_box[(size_t)k * 32] = (uint32_t)to_box((int)(e.x & 0xFFFFu)) | (e.y << 12);
+        }
+    }
     if (tid == 0) {
-        pv.row_ptr[cells] = total;
         PlanHeader h;
-        h.n_pairs = total; h.n_fg = n_fg; h.n_bg_orig = n_bg_orig; h.n_bg_trans = n_bg_trans; h.n_bg_common = n_bg_common;
+        h.n_pairs = n_pairs; h.n_fg = n_fg; h.n_bg_orig = n_bg_orig; h.n_bg_trans = n_bg_trans; h.n_bg_common = n_bg_common;
         h.grid = grid; h.cap = n_fg; h.reserved = 0;
+        h.box_r0 = box_r0; h.box_r1 = box_r1; h.box_s0 = box_s0; h.box_s1 = box_s1;
+        h.n_rows = n_rows; h.n_slices = n_slices; h.n_groups = n_groups; h.pad = 0;
         *pv.hdr = h;
     }
     __syncthreads();
@@ -121,13 +233,10 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     int* co = psm;
     int* ct = psm + cells;
     int* cc = psm + 2 * cells;
-    int* is_src = psm + 3 * cells;
-    for (int i = tid; i < 4 * cells; i += kPlanThreads) psm[i] = 0;
+    int* rowf = psm + 3 * cells;          // cell is a destination row
+    for (int i = tid; i < 3 * cells; i += kPlanThreads) psm[i] = 0;
+    for (int i = tid; i < cells; i += kPlanThreads) rowf[i] = pv.row_ptr[i + 1] > pv.row_ptr[i] ? 1 : 0;
     __syncthreads();
-    for (int n = tid; n < n_fg; n += kPlanThreads) is_src[fg_src[n]] = 1;
-    __shared__ int box_sm[4];
-    __shared__ int nonbin_sm;
-    if (tid == 0) { box_sm[0] = grid; box_sm[1] = -1; box_sm[2] = grid; box_sm[3] = -1; nonbin_sm = 0; }
     for (int n = tid; n < n_bg_orig; n += kPlanThreads) atomicAdd(co + bg_orig[n], 1);
     for (int n = tid; n < n_bg_trans; n += kPlanThreads) atomicAdd(ct + bg_trans[n], 1);
     for (int n = tid; n < n_bg_common; n += kPlanThreads) atomicAdd(cc + bg_common[n], 1);
@@ -138,100 +247,91 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
         v.z = (unsigned short)min(cc[i], 65535); v.w = (unsigned short)(is_src[i] ? 1 : 0);
         pv.bgcnt[i] = v;
         if (co[i] > 1 || ct[i] > 1 || cc[i] > 1) nonbin_sm = 1;
-        if (is_src[i] || pv.row_ptr[i + 1] > pv.row_ptr[i]) {
-            const int r = i / grid, c = i - r * grid;
-            atomicMin(box_sm + 0, r); atomicMax(box_sm + 1, r); atomicMin(box_sm + 2, c); atomicMax(box_sm + 3, c);
-        }
+    }
+    // membership bits of the 16 own cells of every loss-kernel thread (cell 4 * (t + 256 k) + i <-> bit 4 k + i):
+    // x = bg_orig | bg_trans << 16, y = bg_common | destination row << 16
+    if (tid < 256) {
+        uint32_t m_ot = 0, m_cr = 0;
+        for (int k = 0; k < 4; ++k)
+            for (int i = 0; i < 4; ++i) {
+                const int q = 4 * (tid + k * 256) + i, b = 4 * k + i;
+                if (q < cells) {
+                    m_ot |= (co[q] ? 1u : 0u) << b; m_ot |= (ct[q] ? 1u : 0u) << (16 + b);
+                    m_cr |= (cc[q] ? 1u : 0u) << b; m_cr |= (rowf[q] ? 1u : 0u) << (16 + b);
+                }
+            }
+        pv.own_masks[tid] = make_uint2(m_ot, m_cr);
     }
     __syncthreads();
-    if (tid == 0) {
-        pv.hdr->box_r0 = box_sm[0]; pv.hdr->box_r1 = box_sm[1]; pv.hdr->box_s0 = box_sm[2]; pv.hdr->box_s1 = box_sm[3];
-        pv.hdr->reserved = nonbin_sm ? 0 : 1;      // bit 0: every background multiplicity is 0 or 1
-    }
+    if (tid == 0) pv.hdr->reserved = nonbin_sm ? 0 : 1;      // bit 0: every background multiplicity is 0 or 1
 }
 
 // ------------------------------------------------------------------------------------------------
 // fused loss + gradient
 // ------------------------------------------------------------------------------------------------
-// Two kernels share one design: small CTAs (256 threads), many per SM, each walking over (layer, channel) planes.
-//   loss_flat_kernel    layers that already have the loss-grid resolution (64x64): the planes are read straight from
-//                       global memory with 128-bit loads (every cell is needed exactly once for the background sums
-//                       and the gradient), the pair gathers hit the same 32 KB in L1.
-//   loss_resize_kernel  smaller layers (32x32, ...): both planes are staged in shared memory, resized bilinearly
-//                       only inside the box that contains pair cells; the background sums are inner products with
-//                       up^T(multiplicity) at native resolution; the gradient is gathered back through up^T.
-// The sign terms of the foreground pairs are accumulated as INTEGERS (shared-memory atomics): integer addition is
-// associative, so the gradient is bit-reproducible (the reference's index_put(accumulate=True) is not, on CUDA).
-// The last CTA of the last kernel reduces the per-channel partial sums in a fixed order.
 constexpr int kLossThreads = 256;
 constexpr int kLossWarps = kLossThreads / 32;
-constexpr int kOwnGroups = kMaxG * kMaxG / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
-constexpr int kPairUnroll = 4;   // independent pair chains per thread and iteration in the flat kernel (6 and 8 measured equal)
+constexpr int kCtasPerSm = 3;                    // 80 registers per thread; ~64 KB of shared memory per CTA at config-3 sizes
+constexpr int kPlaneCap = kMaxG * kMaxG;         // floats per tensor in the stage
+constexpr int kStageFloats = 2 * kPlaneCap;      // [cur planes][orig planes] = 32 KB
+constexpr int kOwnGroups = kPlaneCap / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
+constexpr int kRowUnroll = 4;    // independent gathers in flight per thread in the row walk
 constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): 2 * G / h <= 16 for h >= 8
+constexpr int kMaxPlanesPerItem = 8;
 
-struct LossLayerDev {
+struct ResizeLayout {   // float offsets into the scratch area
+    int tab, wrow, wcol, uc, uo, cnt, tmp, flat_cnt, total;
+    int box_cap;        // capacity (cells) of the box-local uc / uo / cnt arrays
+};
+
+struct FusedLayer {
     const float* cur;
     const float* orig;
     float* grad;
     int C, h, w;
     float fgw, bgw;
     const void* tab;      // LayerTab of a resized layer (NULL for layers at the loss-grid resolution)
-    int chan_begin;       // first channel id of this layer inside the kernel's own channel range
-    int partial_begin;    // first channel id of this layer in the partial-sum array (all layers)
+    int item_begin;       // first item of this layer among the items of its kind (flat / resized)
+    int ppi;              // planes per item
+    int partial_begin;    // first channel of this layer in the partial-sum array
+    int flat;
 };
 
-struct LossParams {
-    LossLayerDev lv[kMaxLossLayers];
-    int n_layers, total_channels, G;
-    const void* plan;
-    int plan_cap;
+struct FusedParams {
+    FusedLayer lv[kMaxLossLayers];
+    int n_layers, G;
+    int n_flat_items, n_small_items;
+    PlanView pv;        // the plan's arrays (device pointers, resolved on the host)
     int n_fg, n_bg_orig, n_bg_trans, n_bg_common;
     int fg_kind;        // 0 = off, 1 = local_avg patch 1
     int bg_kind;        // 0 = off, 1 = global_avg, 2 = local_avg
     float* partial;     // [all channels][2]: fg sum, bg term
-    unsigned int* work_counter;   // zeroed before the launches: channels beyond the first gridDim.x are handed out dynamically
-};
-
-struct LossFinal {
-    int n_layers, C[kMaxLossLayers], partial_begin[kMaxLossLayers];
-    float fgw[kMaxLossLayers], bgw[kMaxLossLayers];
-    unsigned int* done_counter;       // zeroed before the launches
-    unsigned int total_ctas;          // CTAs of both kernels
+    unsigned int* counters;   // [0] work queue, [1] finished CTAs: zero on entry, re-zeroed by the last CTA
     float* loss_out;
+    ResizeLayout lay;
+    int scratch_floats;
 };
 
-struct ResizeLayout {   // float offsets into dynamic shared memory
-    int tab, wo, wt, planes, uc, uo, cnt, tmp, total;
-    int box_cap;        // capacity (cells) of the box-local uc / uo / cnt arrays
+struct WorkItem {
+    int layer, c0, planes;
 };
 
-__device__ __forceinline__ int layer_of(const LossParams& p, int gc) {
-    int l = 0;
+// Items of the two kinds are interleaved in proportion (Bresenham), so that HBM-heavy 64x64 planes and the
+// arithmetic-heavy resized planes are in flight together from the first to the last item.
+__device__ __forceinline__ WorkItem decode_item(const FusedParams& p, int item) {
+    const int nf = p.n_flat_items, n = nf + p.n_small_items;
+    const int f0 = (int)((unsigned)item * (unsigned)nf / (unsigned)n), f1 = (int)((unsigned)(item + 1) * (unsigned)nf / (unsigned)n);
+    const int flat = f1 > f0;
+    const int idx = flat ? f0 : item - f0;
+    int l = -1;
 #pragma unroll
-    for (int i = 1; i < kMaxLossLayers; ++i)
-        if (i < p.n_layers && gc >= p.lv[i].chan_begin) l = i;
-    return l;
-}
-
-// sum over the CTA of three values, result in every thread; fixed order (warp tree, then a tree over the warp
-// partials that every warp evaluates identically) -> deterministic.  One barrier.
-__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*red)[4]) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
-        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    }
-    if (lane_id() == 0) { red[warp_id()][0] = a; red[warp_id()][1] = b; red[warp_id()][2] = c; }
-    __syncthreads();
-    const float4 r = *reinterpret_cast<const float4*>(red[lane_id() & (kLossWarps - 1)]);
-    a = r.x; b = r.y; c = r.z;
-#pragma unroll
-    for (int o = kLossWarps / 2; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
-        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    }
+    for (int i = 0; i < kMaxLossLayers; ++i)
+        if (i < p.n_layers && p.lv[i].flat == flat && idx >= p.lv[i].item_begin) l = i;
+    WorkItem w;
+    w.layer = l;
+    w.c0 = (idx - p.lv[l].item_begin) * p.lv[l].ppi;
+    w.planes = min(p.lv[l].ppi, p.lv[l].C - w.c0);
+    return w;
 }
 
 __device__ __forceinline__ float block_sum1(float v, float* sm) {
@@ -246,201 +346,68 @@ __device__ __forceinline__ float block_sum1(float v, float* sm) {
     return t;
 }
 
-// Called by every CTA of both kernels when it is done; the last one reduces the per-channel partials in a fixed
-// order -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l.
-__device__ void loss_finish(const LossParams& p, const LossFinal& f, float* red32) {
-    __shared__ unsigned int ticket;
+// Called by the compute warps of every CTA when the queue is empty; the last CTA reduces the per-channel partials in a
+// fixed order -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l, and re-arms the counters.
+__device__ void loss_finish(const FusedParams& p, float* red32, unsigned int* ticket) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) ticket = atomicAdd(f.done_counter, 1u);
+    if (threadIdx.x == 0) *ticket = atomicAdd(p.counters + 1, 1u);
     __syncthreads();
-    if (ticket != f.total_ctas - 1) return;
+    if (*ticket != gridDim.x - 1) return;
     __threadfence();
     float total = 0.0f;
-    for (int l = 0; l < f.n_layers; ++l) {
+    for (int l = 0; l < p.n_layers; ++l) {
+        const FusedLayer& L = p.lv[l];
         float a = 0.0f, b = 0.0f;
-        for (int c = threadIdx.x; c < f.C[l]; c += blockDim.x) {
-            a += __ldcg(p.partial + 2 * (f.partial_begin[l] + c));
-            b += __ldcg(p.partial + 2 * (f.partial_begin[l] + c) + 1);
+        for (int c = threadIdx.x; c < L.C; c += kLossThreads) {
+            a += __ldcg(p.partial + 2 * (L.partial_begin + c));
+            b += __ldcg(p.partial + 2 * (L.partial_begin + c) + 1);
         }
         a = block_sum1(a, red32);
         b = block_sum1(b, red32);
-        const float fg = p.fg_kind ? a / (float)p.n_fg / (float)f.C[l] : 0.0f;
-        const float bg = p.bg_kind == 2 ? b / (float)p.n_bg_common / (float)f.C[l] : (p.bg_kind == 1 ? b / (float)f.C[l] : 0.0f);
-        if (threadIdx.x == 0) { f.loss_out[1 + 2 * l] = fg; f.loss_out[2 + 2 * l] = bg; }
-        if (p.fg_kind) total += f.fgw[l] * fg;
-        if (p.bg_kind) total += f.bgw[l] * bg;
+        const float fg = p.fg_kind ? a / (float)p.n_fg / (float)L.C : 0.0f;
+        const float bg = p.bg_kind == 2 ? b / (float)p.n_bg_common / (float)L.C : (p.bg_kind == 1 ? b / (float)L.C : 0.0f);
+        if (threadIdx.x == 0) { p.loss_out[1 + 2 * l] = fg; p.loss_out[2 + 2 * l] = bg; }
+        if (p.fg_kind) total += L.fgw * fg;
+        if (p.bg_kind) total += L.bgw * bg;
     }
-    if (threadIdx.x == 0) f.loss_out[0] = total;
+    if (threadIdx.x == 0) {
+        p.loss_out[0] = total;
+        p.counters[0] = 0u;       // every CTA has drawn its last item: the queue can be re-armed for the next launch
+        p.counters[1] = 0u;
+    }
 }
 
 __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-
-// ---- layers at the loss-grid resolution -------------------------------------------------------------
-template <bool kBinary>
-__global__ void __launch_bounds__(kLossThreads, 3) loss_flat_kernel(const __grid_constant__ LossParams p,
-                                                                    const __grid_constant__ LossFinal fin) {
-    __shared__ __align__(16) int cnt[kMaxG * kMaxG];
-    __shared__ __align__(16) float red[kLossWarps][4];
-    __shared__ float red32[32];
-    __shared__ float lconst[kMaxLossLayers][4];
-    const int tid = threadIdx.x;
-    const int GG = p.G * p.G;
-    const PlanView pv = plan_view(const_cast<void*>(p.plan), p.G, p.plan_cap);
-    const int n_pairs = pv.hdr->n_pairs;
-    const uint2* __restrict__ pairs = pv.pairs;
-    // membership of the own cells in the three background lists as 16-bit masks (bit 4k+i = cell i of group k).
-    // Lists that come from np.nonzero never repeat a cell; if a generic caller does, the multiplicities are re-read
-    // from the plan in the (slower) general path.
-    uint32_t mo = 0, mt = 0, mc = 0;
-#pragma unroll
-    for (int k = 0; k < kOwnGroups; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = 4 * (tid + k * kLossThreads) + i;
-            if (q < GG) {
-                const ushort4 bc = pv.bgcnt[q];
-                mo |= (bc.x ? 1u : 0u) << (4 * k + i); mt |= (bc.y ? 1u : 0u) << (4 * k + i); mc |= (bc.z ? 1u : 0u) << (4 * k + i);
-            }
-        }
-    auto wgt = [&](uint32_t mask, int k, int i, int which) -> float {     // multiplicity of own cell (k, i) in list `which`
-        if (kBinary) return (float)((mask >> (4 * k + i)) & 1u);
-        const ushort4 bc = pv.bgcnt[4 * (tid + k * kLossThreads) + i];
-        return (float)(which == 0 ? bc.x : which == 1 ? bc.y : bc.z);
-    };
-    if (tid < p.n_layers) {
-        const LossLayerDev& L = p.lv[tid];
-        // an empty index list makes the reference's loss NaN (mean over nothing) but its gradient ZERO: scale 0, not inf
-        lconst[tid][0] = p.fg_kind && p.n_fg > 0 ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
-        lconst[tid][1] = p.bg_kind == 2 && p.n_bg_common > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
-        lconst[tid][2] = p.bg_kind == 1 && p.n_bg_trans > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
-    }
-    const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
-    __syncthreads();
-
-    // dynamic channel queue: the two kernels of one evaluation overlap (programmatic dependent launch), so CTAs start
-    // at different times; the next channel index is fetched while the current channel is processed
-    __shared__ int s_next;
-    int gc = blockIdx.x;
-    while (gc < p.total_channels) {
-        int nxt = 0;
-        if (tid == 0) nxt = (int)atomicAdd(p.work_counter, 1u) + (int)gridDim.x;
-        const int l = layer_of(p, gc);
-        const LossLayerDev& L = p.lv[l];
-        const int c = gc - L.chan_begin;
-        const float* __restrict__ cur = L.cur + (size_t)c * GG;
-        const float* __restrict__ org = L.orig + (size_t)c * GG;
-        // Own cells: four 128-bit groups per thread.  They are consumed right away - background sums, and for the local
-        // background term the sign of (orig - cur) as two bits per cell - so that no plane data stays in registers across
-        // the pair walk (the loads also bring both planes into L1 for the pair gathers).
-        float s1 = 0.0f, s2 = 0.0f;
-        uint32_t sign_pos = 0u, sign_neg = 0u;          // bit 4k+i: orig > cur / orig < cur at own cell i of group k
-#pragma unroll
-        for (int k = 0; k < kOwnGroups; ++k) {
-            const int q = 4 * (tid + k * kLossThreads);
-            if (q < GG) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cur + q));
-                const float4 o4 = __ldg(reinterpret_cast<const float4*>(org + q));
-                *reinterpret_cast<int4*>(cnt + q) = make_int4(0, 0, 0, 0);
-                const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
-                if (p.bg_kind == 1) {
-                    // same association as before: s = fma(w0, v0, fma(w1, v1, fma(w2, v2, fma(w3, v3, s))))
-#pragma unroll
-                    for (int i = 3; i >= 0; --i) {
-                        s1 = fmaf(wgt(mo, k, i, 0), ov[i], s1);
-                        s2 = fmaf(wgt(mt, k, i, 1), cv[i], s2);
-                    }
-                } else if (p.bg_kind == 2) {
-#pragma unroll
-                    for (int i = 3; i >= 0; --i) {
-                        const float d = ov[i] - cv[i];
-                        s1 = fmaf(wgt(mc, k, i, 2), fabsf(d), s1);
-                        sign_pos |= (d > 0.0f ? 1u : 0u) << (4 * k + i);
-                        sign_neg |= (d < 0.0f ? 1u : 0u) << (4 * k + i);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        float acc_f = 0.0f;
-        if (p.fg_kind) {
-            // kPairUnroll independent pair chains per thread and iteration (memory-level parallelism for the L1 gathers)
-            for (int j0 = tid; j0 < n_pairs; j0 += kPairUnroll * kLossThreads) {
-                uint2 e[kPairUnroll];
-                float df[kPairUnroll];
-#pragma unroll
-                for (int u = 0; u < kPairUnroll; ++u) {
-                    const int j = j0 + u * kLossThreads;
-                    e[u] = j < n_pairs ? pairs[j] : make_uint2(0u, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < kPairUnroll; ++u) df[u] = __ldg(org + (e[u].x & 0xFFFFu)) - __ldg(cur + (e[u].x >> 16));
-#pragma unroll
-                for (int u = 0; u < kPairUnroll; ++u) {
-                    acc_f = fmaf((float)e[u].y, fabsf(df[u]), acc_f);
-                    if (df[u] != 0.0f && e[u].y) atomicAdd(cnt + (e[u].x >> 16), df[u] > 0.0f ? -(int)e[u].y : (int)e[u].y);
-                }
-            }
-        }
-        block_sum3(acc_f, s1, s2, red);       // (its barrier also orders the cnt atomics)
-        const float fscale = lconst[l][0], lscale = lconst[l][1], gscale = lconst[l][2];
-        float bg_term = 0.0f, bscale = 0.0f;
-        if (p.bg_kind == 1) {
-            const float delta = s1 * inv_no - s2 * inv_nt;
-            bg_term = fabsf(delta);
-            bscale = -sgn(delta) * gscale;
-        } else if (p.bg_kind == 2) {
-            bg_term = s1;
-        }
-        if (tid == 0) { p.partial[2 * (L.partial_begin + c)] = acc_f; p.partial[2 * (L.partial_begin + c) + 1] = bg_term; }
-        if (L.grad) {
-            float* g = L.grad + (size_t)c * GG;
-#pragma unroll
-            for (int k = 0; k < kOwnGroups; ++k) {
-                const int q = 4 * (tid + k * kLossThreads);
-                if (q >= GG) break;
-                const int4 ci = *reinterpret_cast<const int4*>(cnt + q);
-                float v[4] = {(float)ci.x * fscale, (float)ci.y * fscale, (float)ci.z * fscale, (float)ci.w * fscale};
-                if (p.bg_kind == 1) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = fmaf(wgt(mt, k, i, 1), bscale, v[i]);
-                } else if (p.bg_kind == 2) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float sg = (float)((sign_pos >> (4 * k + i)) & 1u) - (float)((sign_neg >> (4 * k + i)) & 1u);
-                        v[i] -= sg * wgt(mc, k, i, 2) * lscale;
-                    }
-                }
-                st_cs_f4(g + q, make_float4(v[0], v[1], v[2], v[3]));
-            }
-        }
-        if (tid == 0) s_next = nxt;
-        __syncthreads();     // cnt / red are reused by the next channel
-        gc = s_next;
-    }
-    loss_finish(p, fin, red32);
+// snake order of the slices over the compute warps: rounds of kLossWarps slices, every other round reversed, so that the
+// descending slice widths add up to about the same per warp
+__device__ __forceinline__ int slice_of(int round, int wid) {
+    return round * kLossWarps + ((round & 1) ? kLossWarps - 1 - wid : wid);
 }
 
 // ---- layers smaller than the loss grid -----------------------------------------------------------------
-// Per-layer tables, built once per evaluation by loss_resize_setup_kernel (one CTA per resized layer) in global
-// memory and copied to shared memory by every CTA of loss_resize_kernel:
+// Per-layer tables, built once per (plan, layer shape) by loss_resize_setup_kernel in global memory and copied to
+// shared memory by the CTAs of loss_fused_kernel:
 //   bilinear taps of every up row / column, the up rows (columns) that touch each native row (column) with their
 //   weights (the transposed resize in gather form), up^T(background multiplicities) at native resolution, and the
 //   native box that the active up box touches.
-struct LayerTabSmall {
+struct LayerTabHead {      // the part every CTA keeps in shared memory as is
     int ty0[kMaxG], ty1[kMaxG], tx0[kMaxG], tx1[kMaxG];
     float tly[kMaxG], tlx[kMaxG];
     int ylo[kMaxNative], yhi[kMaxNative], xlo[kMaxNative], xhi[kMaxNative];
-    float wrow[kMaxNative * kWin], wcol[kMaxNative * kWin];
     int box[8];                        // up space: r0, r1, s0, s1; native: y0, y1, x0, x1
+    int win, pad_[3];                  // longest window of up rows (columns) that touch one native row (column)
+};
+struct LayerTabSmall : LayerTabHead {
+    float wrow[kMaxNative * kWin], wcol[kMaxNative * kWin];   // stride kWin here, stride `win` in shared memory
 };
 struct LayerTab : LayerTabSmall {
     float wo[kMaxNative * kMaxNative], wt[kMaxNative * kMaxNative];
 };
-static_assert(sizeof(LayerTabSmall) % 16 == 0 && sizeof(LayerTab) % 16 == 0, "tables are copied with 128-bit accesses");
+static_assert(sizeof(LayerTabHead) % 16 == 0 && sizeof(LayerTabSmall) % 16 == 0 && sizeof(LayerTab) % 16 == 0, "tables are copied with 128-bit accesses");
 
 struct SetupParams {
     const void* plan;
@@ -490,6 +457,12 @@ __global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_con
         T.box[6] = any ? T.tx0[s0] : 0; T.box[7] = any ? T.tx1[s1] : -1;
     }
     __syncthreads();
+    if (tid == 0) {
+        int win = 1;
+        for (int i = 0; i < h; ++i) win = max(win, T.yhi[i] - T.ylo[i] + 1);
+        for (int j = 0; j < w; ++j) win = max(win, T.xhi[j] - T.xlo[j] + 1);
+        T.win = win;
+    }
     // wo / wt = up^T applied to the background multiplicities (separable, via tmp)
     for (int pass = 0; pass < 2; ++pass) {
         float* dst = pass == 0 ? T.wo : T.wt;
@@ -513,186 +486,417 @@ __global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_con
     }
 }
 
-struct ResizeShared {
-    float red[kLossWarps][4];
+struct FusedShared {
+    float red[kLossWarps][8];
     float red32[32];
     float lconst[kMaxLossLayers][4];
+    unsigned int ticket;
+    int item, layer, c0, planes;      // the item whose planes are (being) staged, decoded by thread 0
+    uint64_t full;                    // mbarrier: the stage holds `item`
 };
 
-// kG = 64: the loss grid of the reference (shifts instead of integer divisions); kG = 0: any grid <= 64.
-template <int kG>
-__global__ void __launch_bounds__(kLossThreads, 3) loss_resize_kernel(const __grid_constant__ LossParams p,
-                                                                      const __grid_constant__ LossFinal fin,
-                                                                      const __grid_constant__ ResizeLayout lay) {
-    extern __shared__ __align__(16) float rsm[];
-    __shared__ __align__(16) ResizeShared sh;
-    // let the flat-layer kernel of the same evaluation (a programmatic dependent launch) start as soon as SM resources free up
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-    const int G = kG ? kG : p.G, GG = G * G;
-    const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
-    const int n_pairs = pv.hdr->n_pairs;
-    const uint2* __restrict__ pairs = pv.pairs;
-    LayerTabSmall& T = *reinterpret_cast<LayerTabSmall*>(rsm + lay.tab);
-    float* const two = rsm + lay.wo;           // up^T(background multiplicities) of the current layer
-    float* const twt = rsm + lay.wt;
-    float* const planes = rsm + lay.planes;
-    float* const suc = rsm + lay.uc;          // box-local: index (r - br0) * bw + (s - bs0)
-    float* const suo = rsm + lay.uo;
-    int* const cnt = reinterpret_cast<int*>(rsm + lay.cnt);
-    float* const gu = rsm + lay.cnt;
-    float* const tmp = rsm + lay.tmp;
+// sum over the CTA of kN values per thread, results in every thread; fixed order (warp tree, then a tree over the warp
+// partials that every warp evaluates identically) -> deterministic.  One barrier.
+template <int kN>
+__device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8]) {
+    static_assert(kN <= 8, "red holds 8 values per warp");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+    if (lane_id() == 0)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) red[warp_id()][i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = red[lane_id() & (kLossWarps - 1)][i];
+#pragma unroll
+    for (int o = kLossWarps / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+}
 
+// One pair: acc += m |d|, cnt -= m sign(d), with t = copysign(m, d): m |d| = t d, and t is only counted when d != 0.
+// The counts are integer valued floats (|sum| < 2^24, checked on the host): every partial sum is exact, so the order of
+// the additions does not matter and the gradient stays bit-reproducible.
+__device__ __forceinline__ void pair_term(float fm, float d, float& acc, float& cnt) {
+    const float t = copysignf(fm, d);
+    acc = fmaf(t, d, acc);
+    if (d != 0.0f) cnt -= t;
+}
+
+// kG = 64: the loss grid of the reference; kG = 0: any grid <= 64.
+// kBinary: every background multiplicity is 0 or 1 (lists from np.nonzero) -> register bit masks for the own cells.
+template <int kG, bool kBinary, int kCtas>
+__global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(128) float fsm[];
+    __shared__ __align__(16) FusedShared sh;
+    float* const st_cur = fsm;                        // the stage: [cur planes][orig planes]
+    float* const st_org = fsm + kPlaneCap;
+    float* const scratch = fsm + kStageFloats;
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const int n_items = p.n_flat_items + p.n_small_items;
+
+    // Thread 0 is also the producer: it draws the next item from the queue while the current one is processed and, as soon
+    // as every warp is done with the stage, issues the TMA bulk copies of the next item's planes (cp.async.bulk, completion
+    // on the `full` mbarrier).  Several CTAs per SM keep HBM busy while one of them waits.
+    auto stage_item = [&](int item) {
+        sh.item = item;
+        if (item >= n_items) {          // sentinel: the queue is empty
+            mbar_arrive(&sh.full);
+            return;
+        }
+        const WorkItem it = decode_item(p, item);
+        const FusedLayer& L = p.lv[it.layer];
+        sh.layer = it.layer; sh.c0 = it.c0; sh.planes = it.planes;
+        const size_t off = (size_t)it.c0 * L.h * L.w;
+        const uint32_t bytes = (uint32_t)(it.planes * L.h * L.w) * 4u;
+        mbar_arrive_expect_tx(&sh.full, 2u * bytes);
+        tma_bulk_g2s(st_cur, L.cur + off, bytes, &sh.full);
+        tma_bulk_g2s(st_org, L.orig + off, bytes, &sh.full);
+    };
+    if (tid == 0) {
+        mbar_init(&sh.full, 1);
+        mbar_fence_init();
+        stage_item((int)atomicAdd(p.counters, 1u));
+    }
+
+    const int G = kG ? kG : p.G, GG = G * G;
+    const PlanView& pv = p.pv;
+    const int n_slices = p.fg_kind ? pv.hdr->n_slices : 0;
+    const int n_rounds = (n_slices + kLossWarps - 1) / kLossWarps;
+    const int32_t* __restrict__ ell_off = pv.ell_off;
+    // membership of the own cells (flat layers) in the three background lists and in the set of destination rows, as
+    // 16-bit masks (bit 4k+i = cell i of group k), precomputed by the plan.  Lists that come from np.nonzero never repeat a
+    // cell; if a generic caller does, the multiplicities are re-read from the plan in the (slower) general path.
+    const uint2 own = pv.own_masks[tid];
+    const uint32_t m_ot = own.x;                                   // low half: bg_orig, high half: bg_trans
+    const uint32_t m_cr = p.fg_kind ? own.y : (own.y & 0xFFFFu);   // low half: bg_common, high half: destination rows
+    // multiplicity of own cell (k, i) in list `which` (0 = bg_orig, 1 = bg_trans, 2 = bg_common)
+    auto wgt = [&](int k, int i, int which) -> float {
+        if (kBinary) return (float)(((which == 2 ? m_cr : m_ot) >> ((which == 1 ? 16 : 0) + 4 * k + i)) & 1u);
+        const ushort4 bc = pv.bgcnt[4 * (tid + k * kLossThreads) + i];
+        return (float)(which == 0 ? bc.x : which == 1 ? bc.y : bc.z);
+    };
     if (tid < p.n_layers) {
-        const LossLayerDev& L = p.lv[tid];
+        const FusedLayer& L = p.lv[tid];
         // an empty index list makes the reference's loss NaN (mean over nothing) but its gradient ZERO: scale 0, not inf
         sh.lconst[tid][0] = p.fg_kind && p.n_fg > 0 ? L.fgw / ((float)L.C * (float)p.n_fg) : 0.0f;
         sh.lconst[tid][1] = p.bg_kind == 2 && p.n_bg_common > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_common) : 0.0f;
         sh.lconst[tid][2] = p.bg_kind == 1 && p.n_bg_trans > 0 ? L.bgw / ((float)L.C * (float)p.n_bg_trans) : 0.0f;
     }
     const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
-    // the active box is a property of the plan (identical in every layer's table)
-    const LayerTab* tab0 = static_cast<const LayerTab*>(p.lv[0].tab);
-    const int br0 = tab0->box[0], br1 = tab0->box[1], bs0 = tab0->box[2], bs1 = tab0->box[3];
+
+    // resized layers: scratch views and the active box (identical in every layer's table).  Two planes are processed at a
+    // time (float2 per cell), so that the index arithmetic of the resize and of the pair walk is paid once per pair of planes.
+    const ResizeLayout& lay = p.lay;
+    LayerTabHead& T = *reinterpret_cast<LayerTabHead*>(scratch + lay.tab);
+    float* const swrow = scratch + lay.wrow;       // [h][win], [w][win]
+    float* const swcol = scratch + lay.wcol;
+    float2* const suc = reinterpret_cast<float2*>(scratch + lay.uc);     // box-local: index (r - br0) * bw + (s - bs0)
+    float2* const suo = reinterpret_cast<float2*>(scratch + lay.uo);
+    float2* const gu = reinterpret_cast<float2*>(scratch + lay.cnt);     // sign counts, then the gradient w.r.t. up(cur)
+    float2* const tmp = reinterpret_cast<float2*>(scratch + lay.tmp);    // (overlays uc / uo, which are dead by then)
+    float* const cntb = scratch + lay.flat_cnt;                          // sign counts of a flat plane
+    int br0 = 0, br1 = -1, bs0 = 0, bs1 = -1;
+    if (p.n_small_items) {
+        const LayerTab* tab0 = nullptr;
+#pragma unroll
+        for (int i = kMaxLossLayers - 1; i >= 0; --i)
+            if (i < p.n_layers && !p.lv[i].flat) tab0 = static_cast<const LayerTab*>(p.lv[i].tab);
+        br0 = tab0->box[0]; br1 = tab0->box[1]; bs0 = tab0->box[2]; bs1 = tab0->box[3];
+    }
     const bool any_box = br1 >= br0;
     const int bw = any_box ? bs1 - bs0 + 1 : 0, bh = any_box ? br1 - br0 + 1 : 0;
     const int bcells = bw * bh;
+    const bool box_overflow = bcells > lay.box_cap;   // the caller under-sized the box-local buffers: poison, never corrupt
+    // the plan's box-local cell ids are valid when the active box is the plan's box; 'local_avg' works on the whole grid,
+    // where box-local ids are plain cell ids
+    const bool whole_grid = bw == G && bh == G;
+    const uint32_t* __restrict__ s_desc = whole_grid ? pv.row_desc : pv.row_desc_box;
+    const uint32_t* __restrict__ s_ent = whole_grid ? pv.ent : pv.ent_box;
     __syncthreads();
-    if (bcells > lay.box_cap) {      // the caller under-sized the box-local buffers: poison the result instead of corrupting memory
-        for (int gc = blockIdx.x; gc < p.total_channels; gc += gridDim.x)
-            if (tid == 0) {
-                const int l = layer_of(p, gc);
-                p.partial[2 * (p.lv[l].partial_begin + gc - p.lv[l].chan_begin)] = __int_as_float(0x7FC00000);
-                p.partial[2 * (p.lv[l].partial_begin + gc - p.lv[l].chan_begin) + 1] = __int_as_float(0x7FC00000);
-            }
-        loss_finish(p, fin, sh.red32);
-        return;
-    }
 
-    int cur_layer = -1;
-    __shared__ int s_next;
-    int gc = blockIdx.x;
-    while (gc < p.total_channels) {
-        int nxt = 0;
-        if (tid == 0) nxt = (int)atomicAdd(p.work_counter, 1u) + (int)gridDim.x;
-        const int l = layer_of(p, gc);
-        const LossLayerDev& L = p.lv[l];
-        const int c = gc - L.chan_begin;
-        const int h = L.h, w = L.w, hw = h * w;
-        float* const pc_ = planes;
-        float* const po_ = planes + hw;
-        {   // stage both planes (coalesced 128-bit loads)
-            const float4* c4 = reinterpret_cast<const float4*>(L.cur + (size_t)c * hw);
-            const float4* o4 = reinterpret_cast<const float4*>(L.orig + (size_t)c * hw);
-            for (int i = tid; i < hw / 4; i += kLossThreads) {
-                reinterpret_cast<float4*>(pc_)[i] = __ldg(c4 + i);
-                reinterpret_cast<float4*>(po_)[i] = __ldg(o4 + i);
-            }
-            for (int i = tid; i < bcells; i += kLossThreads) cnt[i] = 0;
-        }
-        if (l != cur_layer) {       // (a CTA crosses a layer boundary at most n_layers times)
-            const LayerTab* tl = static_cast<const LayerTab*>(L.tab);
-            const float4* src = reinterpret_cast<const float4*>(static_cast<const LayerTabSmall*>(tl));
-            float4* dst = reinterpret_cast<float4*>(&T);
-            for (int i = tid; i < (int)(sizeof(LayerTabSmall) / 16); i += kLossThreads) dst[i] = src[i];
-            if (p.bg_kind == 1)
-                for (int i = tid; i < hw / 4; i += kLossThreads) {
-                    reinterpret_cast<float4*>(two)[i] = reinterpret_cast<const float4*>(tl->wo)[i];
-                    reinterpret_cast<float4*>(twt)[i] = reinterpret_cast<const float4*>(tl->wt)[i];
-                }
-            cur_layer = l;
-        }
-        __syncthreads();          // planes staged, cnt zeroed, tables loaded
-        const int ny0 = T.box[4], ny1 = T.box[5], nx0 = T.box[6], nx1 = T.box[7];
-        // up(cur), up(orig) inside the box
-        for (int r = br0 + wid; r <= br1; r += kLossWarps) {
-            const int y0 = T.ty0[r] * w, y1 = T.ty1[r] * w;
-            const float ly = T.tly[r], hy = 1.0f - ly;
-            for (int s = bs0 + lane; s <= bs1; s += 32) {
-                const int x0 = T.tx0[s], x1 = T.tx1[s];
-                const float lx = T.tlx[s], hx = 1.0f - lx;
-                const int b = (r - br0) * bw + (s - bs0);
-                suc[b] = hy * (hx * pc_[y0 + x0] + lx * pc_[y0 + x1]) + ly * (hx * pc_[y1 + x0] + lx * pc_[y1 + x1]);
-                suo[b] = hy * (hx * po_[y0 + x0] + lx * po_[y0 + x1]) + ly * (hx * po_[y1 + x0] + lx * po_[y1 + x1]);
-            }
-        }
-        __syncthreads();
-        float acc_f = 0.0f, s1s = 0.0f, s2s = 0.0f;
-        if (p.fg_kind) {
-            const int boff = br0 * bw + bs0;
-            for (int j = tid; j < n_pairs; j += kLossThreads) {
-                const uint2 e = pairs[j];
-                const int d = (int)(e.x >> 16), sc_ = (int)(e.x & 0xFFFFu);
-                const int dr = kG ? d >> 6 : d / G, sr = kG ? sc_ >> 6 : sc_ / G;
-                const int db = dr * bw + (d - dr * G) - boff, sb = sr * bw + (sc_ - sr * G) - boff;
-                const float df = suo[sb] - suc[db];
-                acc_f = fmaf((float)e.y, fabsf(df), acc_f);
-                if (df != 0.0f) atomicAdd(cnt + db, df > 0.0f ? -(int)e.y : (int)e.y);
-            }
-        }
+    int cur_layer = -1;          // resized layer whose tables are in shared memory
+    uint32_t phase = 0;
+    for (;;) {
+        int next_item = 0;
+        if (tid == 0) next_item = (int)atomicAdd(p.counters, 1u);     // (its latency hides behind this item's work)
+        mbar_wait(&sh.full, phase);
+        phase ^= 1;
+        if (sh.item >= n_items) break;
+        const int l = sh.layer, c0 = sh.c0, planes = sh.planes;
+        const FusedLayer& L = p.lv[l];
         const float fscale = sh.lconst[l][0], lscale = sh.lconst[l][1], gscale = sh.lconst[l][2];
-        if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
-            for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
-                const float4 a = *reinterpret_cast<const float4*>(two + i), b = *reinterpret_cast<const float4*>(po_ + i);
-                const float4 e = *reinterpret_cast<const float4*>(twt + i), f = *reinterpret_cast<const float4*>(pc_ + i);
-                s1s = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s1s))));
-                s2s = fmaf(e.x, f.x, fmaf(e.y, f.y, fmaf(e.z, f.z, fmaf(e.w, f.w, s2s))));
-            }
-        } else if (p.bg_kind == 2) {       // box = whole grid
-            for (int q = tid; q < GG; q += kLossThreads) s1s = fmaf((float)pv.bgcnt[q].z, fabsf(suo[q] - suc[q]), s1s);
-        }
-        block_sum3(acc_f, s1s, s2s, sh.red);
-        float bg_term = 0.0f, bscale = 0.0f;
-        if (p.bg_kind == 1) {
-            const float delta = s1s * inv_no - s2s * inv_nt;
-            bg_term = fabsf(delta);
-            bscale = -sgn(delta) * gscale;
-        } else if (p.bg_kind == 2) {
-            bg_term = s1s;
-        }
-        if (tid == 0) { p.partial[2 * (L.partial_begin + c)] = acc_f; p.partial[2 * (L.partial_begin + c) + 1] = bg_term; }
-        if (L.grad) {
-            float* g = L.grad + (size_t)c * hw;
-            // gradient w.r.t. up(cur) inside the box (in place: integer -> float), then up^T in gather form
-            for (int i = tid; i < bcells; i += kLossThreads) {
-                float v = (float)cnt[i] * fscale;
-                if (p.bg_kind == 2) v -= sgn(suo[i] - suc[i]) * (float)pv.bgcnt[i].z * lscale;
-                gu[i] = v;
-            }
-            __syncthreads();
-            for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
-                const int lo = T.ylo[yi];
-                const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
-                const float* wr = T.wrow + yi * kWin - lo;
-                for (int s = bs0 + lane; s <= bs1; s += 32) {
-                    float a = 0.0f;
-                    const float* gp = gu + (s - bs0) - br0 * bw;
-                    for (int r = ra; r <= rb; ++r) a = fmaf(wr[r], gp[r * bw], a);
-                    tmp[yi * G + s] = a;
-                }
-            }
-            __syncthreads();
-            for (int yi = wid; yi < h; yi += kLossWarps) {
-                const bool row_in = yi >= ny0 && yi <= ny1;
-                for (int xj = lane; xj < w; xj += 32) {
-                    float a = 0.0f;
-                    if (row_in && xj >= nx0 && xj <= nx1) {
-                        const int lo = T.xlo[xj];
-                        const int sa = max(lo, bs0), sb = min(T.xhi[xj], bs1);
-                        const float* wc = T.wcol + xj * kWin - lo;
-                        const float* tp = tmp + yi * G;
-                        for (int s = sa; s <= sb; ++s) a = fmaf(wc[s], tp[s], a);
+        if (L.flat) {
+            // ------------------------------------------------------------------ a plane at the loss-grid resolution
+            const int c = c0;
+            // Own cells: four 128-bit groups per thread, consumed right away - background sums, and for the local
+            // background term the sign of (orig - cur) as two bits per cell.
+            float sums[3] = {0.0f, 0.0f, 0.0f};          // foreground sum, two background sums
+            uint32_t sign_bits = 0u;          // bit 4k+i: orig > cur, bit 16+4k+i: orig < cur at own cell i of group k
+            if (p.bg_kind) {
+#pragma unroll
+                for (int k = 0; k < kOwnGroups; ++k) {
+                    const int q = 4 * (tid + k * kLossThreads);
+                    if (q < GG) {
+                        const float4 c4 = *reinterpret_cast<const float4*>(st_cur + q);
+                        const float4 o4 = *reinterpret_cast<const float4*>(st_org + q);
+                        const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+                        if (p.bg_kind == 1) {
+#pragma unroll
+                            for (int i = 3; i >= 0; --i) {
+                                if (kBinary) {      // (adding x is fmaf(1, x, s); skipping it is fmaf(0, x, s) for finite x)
+                                    if ((m_ot >> (4 * k + i)) & 1u) sums[1] += ov[i];
+                                    if ((m_ot >> (16 + 4 * k + i)) & 1u) sums[2] += cv[i];
+                                } else {
+                                    sums[1] = fmaf(wgt(k, i, 0), ov[i], sums[1]);
+                                    sums[2] = fmaf(wgt(k, i, 1), cv[i], sums[2]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 3; i >= 0; --i) {
+                                const float d = ov[i] - cv[i];
+                                sums[1] = fmaf(wgt(k, i, 2), fabsf(d), sums[1]);
+                                sign_bits |= (d > 0.0f ? 1u : 0u) << (4 * k + i);
+                                sign_bits |= (d < 0.0f ? 1u : 0u) << (16 + 4 * k + i);
+                            }
+                        }
                     }
-                    if (p.bg_kind == 1) a = fmaf(bscale, twt[yi * w + xj], a);
-                    g[yi * w + xj] = a;
+                }
+            }
+            // the scratch area may still be read by slow warps (sign counts of the previous plane, a resized plane's buffers)
+            __syncthreads();
+            // Destination rows: one thread per destination cell, its sources from the sliced-ELL plan
+            for (int rd = 0; rd < n_rounds; ++rd) {
+                const int sl = slice_of(rd, wid);
+                if (sl >= n_slices) break;
+                const uint32_t desc = __ldg(pv.row_desc + sl * 32 + lane);
+                const int len = (int)(desc >> 16), dcell = (int)(desc & 0xFFFFu);
+                const uint32_t* __restrict__ e_ptr = pv.ent + (size_t)__ldg(ell_off + sl) * 32 + lane;
+                const float cval = st_cur[dcell];
+                float cn = 0.0f;
+                for (int k = 0; k < len; k += kRowUnroll) {
+                    uint32_t e[kRowUnroll];
+                    float o[kRowUnroll];
+#pragma unroll
+                    for (int u = 0; u < kRowUnroll; ++u) e[u] = k + u < len ? __ldg(e_ptr + (k + u) * 32) : 0u;
+#pragma unroll
+                    for (int u = 0; u < kRowUnroll; ++u) o[u] = st_org[e[u] & 0xFFFu];
+#pragma unroll
+                    for (int u = 0; u < kRowUnroll; ++u) pair_term((float)(e[u] >> 12), o[u] - cval, sums[0], cn);   // (m = 0: no-op)
+                }
+                if (len) cntb[dcell] = cn;
+            }
+            block_sum<3>(sums, sh.red);       // (its barrier also orders the count stores and ends the reads of the stage)
+            if (tid == 0) stage_item(next_item);
+            float bg_term = 0.0f, bscale = 0.0f;
+            if (p.bg_kind == 1) {
+                const float delta = sums[1] * inv_no - sums[2] * inv_nt;
+                bg_term = fabsf(delta);
+                bscale = -sgn(delta) * gscale;
+            } else if (p.bg_kind == 2) {
+                bg_term = sums[1];
+            }
+            if (tid == 0) { p.partial[2 * (L.partial_begin + c)] = sums[0]; p.partial[2 * (L.partial_begin + c) + 1] = bg_term; }
+            if (L.grad) {
+                float* g = L.grad + (size_t)c * GG;
+#pragma unroll
+                for (int k = 0; k < kOwnGroups; ++k) {
+                    const int q = 4 * (tid + k * kLossThreads);
+                    if (q >= GG) break;
+                    const float4 ci = *reinterpret_cast<const float4*>(cntb + q);     // cells that are no row hold stale data: masked
+                    const float cv[4] = {ci.x, ci.y, ci.z, ci.w};
+                    float v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = ((m_cr >> (16 + 4 * k + i)) & 1u) ? cv[i] * fscale : 0.0f;
+                    if (p.bg_kind == 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (kBinary) { if ((m_ot >> (16 + 4 * k + i)) & 1u) v[i] += bscale; }
+                            else v[i] = fmaf(wgt(k, i, 1), bscale, v[i]);
+                        }
+                    } else if (p.bg_kind == 2) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float sg = (float)((sign_bits >> (4 * k + i)) & 1u) - (float)((sign_bits >> (16 + 4 * k + i)) & 1u);
+                            v[i] -= sg * wgt(k, i, 2) * lscale;
+                        }
+                    }
+                    st_cs_f4(g + q, make_float4(v[0], v[1], v[2], v[3]));
+                }
+            }
+        } else {
+            // ------------------------------------------------------------------ planes of a layer below the loss grid
+            const int h = L.h, w = L.w, hw = h * w;
+            const LayerTab* const tl = static_cast<const LayerTab*>(L.tab);
+            const float* __restrict__ gwo = tl->wo;      // up^T(background multiplicities), read through L1
+            const float* __restrict__ gwt = tl->wt;
+            if (l != cur_layer) {       // (a CTA crosses a layer boundary a handful of times)
+                __syncthreads();        // slow warps may still read the previous layer's tables
+                const float4* src = reinterpret_cast<const float4*>(static_cast<const LayerTabHead*>(tl));
+                float4* dst = reinterpret_cast<float4*>(&T);
+                for (int i = tid; i < (int)(sizeof(LayerTabHead) / 16); i += kLossThreads) dst[i] = src[i];
+                const int win = tl->win;
+                for (int i = tid; i < h * win; i += kLossThreads) swrow[i] = tl->wrow[(i / win) * kWin + i % win];
+                for (int i = tid; i < w * win; i += kLossThreads) swcol[i] = tl->wcol[(i / win) * kWin + i % win];
+                cur_layer = l;
+            }
+            for (int pl = 0; pl < planes; pl += 2) {
+                const int c = c0 + pl;
+                const bool two = pl + 1 < planes;          // an odd plane at the end is paired with itself, its copy is not stored
+                const float* const pc0 = st_cur + pl * hw;
+                const float* const po0 = st_org + pl * hw;
+                const float* const pc1 = two ? pc0 + hw : pc0;
+                const float* const po1 = two ? po0 + hw : po0;
+                const bool last_pair = pl + 2 >= planes;
+                __syncthreads();          // tables loaded; scratch of the previous pair / flat item no longer read
+                if (box_overflow) {
+                    if (tid == 0) {
+                        for (int j = 0; j < (two ? 2 : 1); ++j) {
+                            p.partial[2 * (L.partial_begin + c + j)] = __int_as_float(0x7FC00000);
+                            p.partial[2 * (L.partial_begin + c + j) + 1] = __int_as_float(0x7FC00000);
+                        }
+                        if (last_pair) stage_item(next_item);
+                    }
+                    continue;
+                }
+                const int win = T.win;
+                const int ny0 = T.box[4], ny1 = T.box[5], nx0 = T.box[6], nx1 = T.box[7];
+                // up(cur), up(orig) inside the box (and the box-local sign counts start at zero)
+                for (int i = tid; i < bcells; i += kLossThreads) gu[i] = make_float2(0.0f, 0.0f);
+                for (int r = br0 + wid; r <= br1; r += kLossWarps) {
+                    const int y0 = T.ty0[r] * w, y1 = T.ty1[r] * w;
+                    const float ly = T.tly[r], hy = 1.0f - ly;
+                    for (int s = bs0 + lane; s <= bs1; s += 32) {
+                        const int x0 = T.tx0[s], x1 = T.tx1[s];
+                        const float lx = T.tlx[s], hx = 1.0f - lx;
+                        const int b = (r - br0) * bw + (s - bs0);
+                        const int i00 = y0 + x0, i01 = y0 + x1, i10 = y1 + x0, i11 = y1 + x1;
+                        suc[b] = make_float2(hy * (hx * pc0[i00] + lx * pc0[i01]) + ly * (hx * pc0[i10] + lx * pc0[i11]),
+                                             hy * (hx * pc1[i00] + lx * pc1[i01]) + ly * (hx * pc1[i10] + lx * pc1[i11]));
+                        suo[b] = make_float2(hy * (hx * po0[i00] + lx * po0[i01]) + ly * (hx * po0[i10] + lx * po0[i11]),
+                                             hy * (hx * po1[i00] + lx * po1[i01]) + ly * (hx * po1[i10] + lx * po1[i11]));
+                    }
+                }
+                __syncthreads();
+                float sums[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // per plane: foreground sum, two background sums
+                for (int rd = 0; rd < n_rounds; ++rd) {
+                    const int sl = slice_of(rd, wid);
+                    if (sl >= n_slices) break;
+                    const uint32_t desc = __ldg(s_desc + sl * 32 + lane);
+                    const int len = (int)(desc >> 16), db = (int)(desc & 0xFFFFu);
+                    const uint32_t* __restrict__ e_ptr = s_ent + (size_t)__ldg(ell_off + sl) * 32 + lane;
+                    const float2 cval = suc[db];
+                    float cn0 = 0.0f, cn1 = 0.0f;
+                    for (int k = 0; k < len; k += kRowUnroll) {
+                        uint32_t e[kRowUnroll];
+                        float2 o[kRowUnroll];
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) e[u] = k + u < len ? __ldg(e_ptr + (k + u) * 32) : 0u;
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) o[u] = suo[e[u] & 0xFFFu];
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) {
+                            const float fm = (float)(e[u] >> 12);          // (m = 0 past the end of the row: no-op)
+                            pair_term(fm, o[u].x - cval.x, sums[0], cn0);
+                            pair_term(fm, o[u].y - cval.y, sums[3], cn1);
+                        }
+                    }
+                    if (len) gu[db] = make_float2(cn0, cn1);
+                }
+                if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
+                    for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(gwo + i)), e = __ldg(reinterpret_cast<const float4*>(gwt + i));
+                        const float4 b0 = *reinterpret_cast<const float4*>(po0 + i), f0 = *reinterpret_cast<const float4*>(pc0 + i);
+                        const float4 b1 = *reinterpret_cast<const float4*>(po1 + i), f1 = *reinterpret_cast<const float4*>(pc1 + i);
+                        sums[1] = fmaf(a.x, b0.x, fmaf(a.y, b0.y, fmaf(a.z, b0.z, fmaf(a.w, b0.w, sums[1]))));
+                        sums[2] = fmaf(e.x, f0.x, fmaf(e.y, f0.y, fmaf(e.z, f0.z, fmaf(e.w, f0.w, sums[2]))));
+                        sums[4] = fmaf(a.x, b1.x, fmaf(a.y, b1.y, fmaf(a.z, b1.z, fmaf(a.w, b1.w, sums[4]))));
+                        sums[5] = fmaf(e.x, f1.x, fmaf(e.y, f1.y, fmaf(e.z, f1.z, fmaf(e.w, f1.w, sums[5]))));
+                    }
+                } else if (p.bg_kind == 2) {       // box = whole grid
+                    for (int q = tid; q < GG; q += kLossThreads) {
+                        const float mz = (float)pv.bgcnt[q].z;
+                        const float2 uo = suo[q], uc = suc[q];
+                        sums[1] = fmaf(mz, fabsf(uo.x - uc.x), sums[1]);
+                        sums[4] = fmaf(mz, fabsf(uo.y - uc.y), sums[4]);
+                    }
+                }
+                block_sum<6>(sums, sh.red);
+                if (last_pair && tid == 0) stage_item(next_item);      // every read of the staged planes is behind the barrier
+                float bscale0 = 0.0f, bscale1 = 0.0f;
+                {
+                    float bg0 = 0.0f, bg1 = 0.0f;
+                    if (p.bg_kind == 1) {
+                        const float d0 = sums[1] * inv_no - sums[2] * inv_nt, d1 = sums[4] * inv_no - sums[5] * inv_nt;
+                        bg0 = fabsf(d0); bg1 = fabsf(d1);
+                        bscale0 = -sgn(d0) * gscale; bscale1 = -sgn(d1) * gscale;
+                    } else if (p.bg_kind == 2) {
+                        bg0 = sums[1]; bg1 = sums[4];
+                    }
+                    if (tid == 0) {
+                        p.partial[2 * (L.partial_begin + c)] = sums[0]; p.partial[2 * (L.partial_begin + c) + 1] = bg0;
+                        if (two) { p.partial[2 * (L.partial_begin + c + 1)] = sums[3]; p.partial[2 * (L.partial_begin + c + 1) + 1] = bg1; }
+                    }
+                }
+                if (L.grad) {
+                    float* g0 = L.grad + (size_t)c * hw;
+                    // gradient w.r.t. up(cur) inside the box (in place: sign count -> gradient), then up^T in gather form
+                    for (int i = tid; i < bcells; i += kLossThreads) {
+                        float2 v = gu[i];
+                        v.x *= fscale; v.y *= fscale;
+                        if (p.bg_kind == 2) {
+                            const float mz = (float)pv.bgcnt[i].z * lscale;
+                            const float2 uo = suo[i], uc = suc[i];
+                            v.x -= sgn(uo.x - uc.x) * mz; v.y -= sgn(uo.y - uc.y) * mz;
+                        }
+                        gu[i] = v;
+                    }
+                    __syncthreads();
+                    for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
+                        const int lo = T.ylo[yi];
+                        const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
+                        const float* wr = swrow + yi * win - lo;
+                        for (int s = bs0 + lane; s <= bs1; s += 32) {
+                            float a0 = 0.0f, a1 = 0.0f;
+                            const float2* gp = gu + (s - bs0) - br0 * bw;
+                            for (int r = ra; r <= rb; ++r) {
+                                const float2 gv = gp[r * bw];
+                                a0 = fmaf(wr[r], gv.x, a0); a1 = fmaf(wr[r], gv.y, a1);
+                            }
+                            tmp[yi * G + s] = make_float2(a0, a1);
+                        }
+                    }
+                    __syncthreads();
+                    for (int yi = wid; yi < h; yi += kLossWarps) {
+                        const bool row_in = yi >= ny0 && yi <= ny1;
+                        for (int xj = lane; xj < w; xj += 32) {
+                            float a0 = 0.0f, a1 = 0.0f;
+                            if (row_in && xj >= nx0 && xj <= nx1) {
+                                const int lo = T.xlo[xj];
+                                const int sa = max(lo, bs0), sb = min(T.xhi[xj], bs1);
+                                const float* wc = swcol + xj * win - lo;
+                                const float2* tp = tmp + yi * G;
+                                for (int s = sa; s <= sb; ++s) {
+                                    const float2 tv = tp[s];
+                                    a0 = fmaf(wc[s], tv.x, a0); a1 = fmaf(wc[s], tv.y, a1);
+                                }
+                            }
+                            if (p.bg_kind == 1) {
+                                const float wtv = __ldg(gwt + yi * w + xj);
+                                a0 = fmaf(bscale0, wtv, a0); a1 = fmaf(bscale1, wtv, a1);
+                            }
+                            g0[yi * w + xj] = a0;
+                            if (two) g0[hw + yi * w + xj] = a1;
+                        }
+                    }
                 }
             }
         }
-        if (tid == 0) s_next = nxt;
-        __syncthreads();     // planes / cnt / uc / tmp are reused by the next channel
-        gc = s_next;
     }
-    loss_finish(p, fin, sh.red32);
+    loss_finish(p, sh.red32, &sh.ticket);
 }
 
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, size_t n, const float* __restrict__ scale) {
@@ -742,13 +946,12 @@ extern "C" {
 
 size_t dh_loss_plan_bytes(int grid, int n_fg) {
     if (grid < 1 || grid > kMaxG || n_fg < 0) return 0;
-    size_t a, b, c;
-    return plan_layout(grid, n_fg, &a, &b, &c);
+    return plan_layout(grid, n_fg).total;
 }
 
 size_t dh_loss_plan_workspace_bytes(int grid, int n_fg) {
     if (grid < 1 || grid > kMaxG || n_fg < 0) return 0;
-    return sizeof(int32_t) * (size_t)(n_fg > 0 ? n_fg : 1);
+    return sizeof(int32_t) * 2 * (size_t)(n_fg > 0 ? n_fg : 1);
 }
 
 int dh_build_loss_plan(const int32_t* fg_src, const int32_t* fg_dst, int n_fg, const int32_t* bg_orig, int n_bg_orig,
@@ -760,7 +963,10 @@ int dh_build_loss_plan(const int32_t* fg_src, const int32_t* fg_dst, int n_fg, c
     DH_REQUIRE((bg_orig || n_bg_orig == 0) && (bg_trans || n_bg_trans == 0) && (bg_common || n_bg_common == 0));
     if (plan_bytes < dh_loss_plan_bytes(grid, n_fg) || ws_bytes < dh_loss_plan_workspace_bytes(grid, n_fg)) return DH_ERR_WORKSPACE;
     const int cells = grid * grid;
-    const size_t smem = sizeof(int) * ((size_t)3 * cells + 1) + sizeof(uint32_t) * (size_t)kPlanCountWarps * cells;
+    size_t smem_ints = (size_t)3 * cells + 1 + (size_t)kPlanWarps * kPlanTab;
+    if (smem_ints < (size_t)4 * cells) smem_ints = (size_t)4 * cells;
+    const size_t smem = sizeof(int) * smem_ints;
+    static_assert(kPlanWarps * kPlanTab >= 2 * kPlanWarps * kLenClasses, "the ELL histograms live in the counter tables");
     DH_CUDA_CHECK(cudaFuncSetAttribute(loss_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     loss_plan_kernel<<<1, kPlanThreads, smem, as_stream(stream)>>>(fg_src, fg_dst, n_fg, bg_orig, n_bg_orig, bg_trans, n_bg_trans,
                                                                    bg_common, n_bg_common, grid, plan, static_cast<int32_t*>(ws));
@@ -787,7 +993,6 @@ int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int
     DH_REQUIRE(plan && tables && grid >= 1 && grid <= kMaxG && h >= 1 && w >= 1 && n_fg >= 0);
     if (h > grid || w > grid || h > kMaxNative || w > kMaxNative) return DH_ERR_UNSUPPORTED;
     if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
-    if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
     SetupParams sp;
     sp.plan = plan; sp.plan_cap = n_fg; sp.G = grid; sp.h = h; sp.w = w; sp.fg_kind = fg_kind; sp.bg_kind = bg_kind;
     loss_resize_setup_kernel<<<1, 256, 0, as_stream(stream)>>>(sp, static_cast<LayerTab*>(tables));
@@ -812,58 +1017,90 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     DH_REQUIRE(n_fg >= 0 && n_bg_orig >= 0 && n_bg_trans >= 0 && n_bg_common >= 0);
     if (bg_kind != 0 && bg_kind != 1 && bg_kind != 2) return DH_ERR_INVALID_ARGUMENT;
     if (fg_kind != 0 && fg_kind != 1) return DH_ERR_INVALID_ARGUMENT;
-    LossParams pf, pr;      // flat (native == grid) and resized layers
-    LossFinal fin;
-    memset(&pf, 0, sizeof(pf));
-    memset(&pr, 0, sizeof(pr));
-    memset(&fin, 0, sizeof(fin));
-    int chan = 0, hw_r = 0, h_r = 0;
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    const int GG = grid * grid;
+    int chan = 0, h_r = 0, wrow_floats = 0, wcol_floats = 0;
     for (int i = 0; i < n_layers; ++i) {
         const dh_loss_layer& s = layers_host[i];
         DH_REQUIRE(s.cur && s.orig && s.channels >= 1 && s.h >= 1 && s.w >= 1);
         if (s.h > kMaxNative || s.w > kMaxNative || s.h > grid || s.w > grid) return DH_ERR_UNSUPPORTED;
         // the transposed-resize tables hold kWin up rows (columns) per native row (column): 2 * ceil(grid / h) of them are needed
         if (2 * ((grid + s.h - 1) / s.h) > kWin || 2 * ((grid + s.w - 1) / s.w) > kWin) return DH_ERR_UNSUPPORTED;
-        if (((size_t)s.h * s.w) % 4 != 0) return DH_ERR_UNSUPPORTED;     // 128-bit plane loads
+        if (((size_t)s.h * s.w) % 4 != 0) return DH_ERR_UNSUPPORTED;     // 16-byte bulk copies, 128-bit plane accesses
         if ((reinterpret_cast<uintptr_t>(s.cur) & 15) || (reinterpret_cast<uintptr_t>(s.orig) & 15) ||
             (s.grad && (reinterpret_cast<uintptr_t>(s.grad) & 15)))
             return DH_ERR_INVALID_ARGUMENT;
         const bool flat = s.h == grid && s.w == grid;
-        if (flat && (grid * grid) % 4 != 0) return DH_ERR_UNSUPPORTED;
         if (!flat && (!s.resize_tables || (reinterpret_cast<uintptr_t>(s.resize_tables) & 15))) return DH_ERR_INVALID_ARGUMENT;
-        LossParams& q = flat ? pf : pr;
-        LossLayerDev& L = q.lv[q.n_layers++];
+        FusedLayer& L = fp.lv[i];
         L.cur = s.cur; L.orig = s.orig; L.grad = s.grad;
         L.C = s.channels; L.h = s.h; L.w = s.w; L.fgw = s.fg_weight; L.bgw = s.bg_weight;
         L.tab = flat ? nullptr : s.resize_tables;
-        L.chan_begin = q.total_channels;
+        L.flat = flat ? 1 : 0;
         L.partial_begin = chan;
-        q.total_channels += s.channels;
-        fin.C[i] = s.channels; fin.partial_begin[i] = chan; fin.fgw[i] = s.fg_weight; fin.bgw[i] = s.bg_weight;
         chan += s.channels;
-        if (!flat) {
-            if (s.h * s.w > hw_r) hw_r = s.h * s.w;
+        if (flat) {
+            L.ppi = 1;
+            L.item_begin = fp.n_flat_items;
+            fp.n_flat_items += s.channels;
+        } else {
+            int ppi = kPlaneCap / (s.h * s.w);
+            if (ppi > kMaxPlanesPerItem) ppi = kMaxPlanesPerItem;
+            if (ppi < 1) ppi = 1;
+            L.ppi = ppi;
+            L.item_begin = fp.n_small_items;
+            fp.n_small_items += (s.channels + ppi - 1) / ppi;
             if (s.h > h_r) h_r = s.h;
+            // rows of the transposed-resize tables in shared memory: at most 2 * ceil(grid / h) up rows touch one native row
+            const int wy = 2 * ((grid + s.h - 1) / s.h) < kWin ? 2 * ((grid + s.h - 1) / s.h) : kWin;
+            const int wx = 2 * ((grid + s.w - 1) / s.w) < kWin ? 2 * ((grid + s.w - 1) / s.w) : kWin;
+            const int wmax = wy > wx ? wy : wx;       // the tables share one stride
+            if (s.h * wmax > wrow_floats) wrow_floats = s.h * wmax;
+            if (s.w * wmax > wcol_floats) wcol_floats = s.w * wmax;
         }
     }
-    fin.n_layers = n_layers;
+    if (fp.n_flat_items + fp.n_small_items > 46000) return DH_ERR_UNSUPPORTED;      // 32-bit item interleave arithmetic
+    fp.n_layers = n_layers;
+    fp.G = grid;
     size_t o_counter;
     if (ws_bytes < loss_ws_layout((size_t)chan, &o_counter)) return DH_ERR_WORKSPACE;
-    for (LossParams* q : {&pf, &pr}) {
-        q->G = grid; q->plan = plan; q->plan_cap = n_fg;
-        q->n_fg = n_fg; q->n_bg_orig = n_bg_orig; q->n_bg_trans = n_bg_trans; q->n_bg_common = n_bg_common;
-        q->fg_kind = fg_kind; q->bg_kind = bg_kind;
-        q->partial = static_cast<float*>(ws);
+    fp.pv = plan_view(const_cast<void*>(plan), grid, n_fg);
+    if (n_fg >= (1 << 24)) return DH_ERR_UNSUPPORTED;      // sign counts are integer valued floats
+    fp.n_fg = n_fg; fp.n_bg_orig = n_bg_orig; fp.n_bg_trans = n_bg_trans; fp.n_bg_common = n_bg_common;
+    fp.fg_kind = fg_kind; fp.bg_kind = bg_kind;
+    fp.partial = static_cast<float*>(ws);
+    fp.counters = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
+    fp.loss_out = loss_out;
+    // scratch: the tables of the current resized layer, then the per-plane buffers of a resized plane overlaid with the
+    // sign-count buffer of a flat plane
+    auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+    ResizeLayout& lay = fp.lay;
+    int o = 0;
+    if (fp.n_small_items) {
+        int cap = (box_cells > 0 && box_cells <= GG && bg_kind != 2) ? box_cells : GG;
+        if (!fg_kind && bg_kind != 2) cap = 4;
+        lay.tab = o;    o += (int)(sizeof(LayerTabHead) / 4);
+        lay.wrow = o;   o += up4(wrow_floats);
+        lay.wcol = o;   o += up4(wcol_floats);
+        // two planes at a time: float2 per box cell.  tmp (2 * h * grid floats) is written when uc / uo are dead
+        const int plane_area = 4 * up4(cap) > 2 * up4(h_r * grid) ? 4 * up4(cap) : 2 * up4(h_r * grid);
+        lay.uc = o;     lay.uo = o + 2 * up4(cap);  lay.tmp = o;   o += plane_area;
+        lay.cnt = o;    o += 2 * up4(cap);
+        lay.box_cap = cap;
     }
-    fin.done_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
-    pf.work_counter = fin.done_counter + 1;
-    pr.work_counter = fin.done_counter + 2;
-    fin.loss_out = loss_out;
+    lay.flat_cnt = fp.n_small_items ? lay.uc : 0;
+    if (fp.n_flat_items && lay.flat_cnt + GG > o) o = lay.flat_cnt + GG;
+    lay.total = o;
+    fp.scratch_floats = up4(o);
+    const size_t smem = sizeof(float) * ((size_t)kStageFloats + fp.scratch_floats);
     cudaStream_t st = as_stream(stream);
     // per-process caches of the launch geometry queries (this entry point runs every denoising step)
     struct LaunchCache {
-        int sms, occ_flat[2], occ_resize[2];
-        size_t occ_resize_smem[2], smem_attr_set[2];
+        int sms;
+        size_t smem_attr_set[8];
+        int occ[8];
+        size_t occ_smem[8];
     };
     static LaunchCache caches[64];          // zero-initialised; one entry per device (function attributes are per device)
     int dev = 0;
@@ -871,77 +1108,32 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     if (dev < 0 || dev >= 64) return DH_ERR_UNSUPPORTED;
     LaunchCache& lc = caches[dev];
     if (!lc.sms) DH_CUDA_CHECK(cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev));
-    const int sms = lc.sms;
-    int (&occ_flat)[2] = lc.occ_flat;
-    int (&occ_resize)[2] = lc.occ_resize;
-    size_t (&occ_resize_smem)[2] = lc.occ_resize_smem;
-    size_t (&smem_attr_set)[2] = lc.smem_attr_set;
-    // grids: persistent CTAs, as many as fit per SM
-    int grid_f = 0, grid_r = 0;
-    ResizeLayout lay;
-    memset(&lay, 0, sizeof(lay));
-    size_t smem_r = 0;
     // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
-    auto flat_kernel = (plan_flags & 1) ? loss_flat_kernel<true> : loss_flat_kernel<false>;
-    if (pf.total_channels) {
-        int& per_sm = occ_flat[(plan_flags & 1) ? 1 : 0];
-        if (!per_sm) {
-            DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_kernel, kLossThreads, 0));
-            if (per_sm < 1) per_sm = 1;
-        }
-        grid_f = sms * per_sm;
-        if (grid_f > pf.total_channels) grid_f = pf.total_channels;
+    static int ctas_env = -1;
+    if (ctas_env < 0) {
+        const char* e = getenv("DH_LOSS_CTAS");
+        ctas_env = e && atoi(e) == 4 ? 4 : kCtasPerSm;
     }
-    auto resize_kernel = grid == 64 ? loss_resize_kernel<64> : loss_resize_kernel<0>;
-    if (pr.total_channels) {
-        const int GG = grid * grid;
-        auto up4 = [](int v) { return (v + 3) / 4 * 4; };
-        int cap = (box_cells > 0 && box_cells <= GG && bg_kind != 2) ? box_cells : GG;
-        if (!fg_kind && bg_kind != 2) cap = 4;
-        int o = 0;
-        lay.tab = o;    o += (int)(sizeof(LayerTabSmall) / 4);
-        lay.wo = o;     o += up4(hw_r);
-        lay.wt = o;     o += up4(hw_r);
-        lay.planes = o; o += up4(2 * hw_r);
-        lay.uc = o;     o += up4(cap);
-        lay.uo = o;     o += up4(cap);
-        lay.cnt = o;    o += up4(cap);
-        lay.tmp = o;    o += up4(h_r * grid);
-        lay.total = o;
-        lay.box_cap = cap;
-        smem_r = sizeof(float) * (size_t)o;
-        const int rk = grid == 64 ? 1 : 0;
-        if (smem_r > smem_attr_set[rk]) {
-            DH_CUDA_CHECK(cudaFuncSetAttribute(resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-            smem_attr_set[rk] = smem_r;
-        }
-        if (!occ_resize[rk] || occ_resize_smem[rk] != smem_r) {
-            int per_sm = 1;
-            DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resize_kernel, kLossThreads, smem_r));
-            occ_resize[rk] = per_sm < 1 ? 1 : per_sm;
-            occ_resize_smem[rk] = smem_r;
-        }
-        grid_r = sms * occ_resize[rk];
-        if (grid_r > pr.total_channels) grid_r = pr.total_channels;
+    const int vi = (grid == 64 ? 2 : 0) + ((plan_flags & 1) ? 1 : 0) + (ctas_env == 3 ? 4 : 0);   // bit 2: three CTAs per SM
+    void (*kernel)(const FusedParams) =
+        vi == 3 ? loss_fused_kernel<64, true, 4> : vi == 2 ? loss_fused_kernel<64, false, 4> : vi == 1 ? loss_fused_kernel<0, true, 4>
+        : vi == 0 ? loss_fused_kernel<0, false, 4> : vi == 7 ? loss_fused_kernel<64, true, 3> : vi == 6 ? loss_fused_kernel<64, false, 3>
+        : vi == 5 ? loss_fused_kernel<0, true, 3> : loss_fused_kernel<0, false, 3>;
+    if (smem > lc.smem_attr_set[vi]) {
+        DH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lc.smem_attr_set[vi] = smem;
     }
-    fin.total_ctas = (unsigned int)(grid_f + grid_r);
-    DH_CUDA_CHECK(cudaMemsetAsync(fin.done_counter, 0, 4 * sizeof(unsigned int), st));
-    if (grid_r) {
-        resize_kernel<<<grid_r, kLossThreads, smem_r, st>>>(pr, fin, lay);
-        DH_LAUNCH_CHECK();
+    if (!lc.occ[vi] || lc.occ_smem[vi] != smem) {
+        int per_sm = 1;
+        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLossThreads, smem));
+        lc.occ[vi] = per_sm < 1 ? 1 : per_sm;
+        lc.occ_smem[vi] = smem;
     }
-    if (grid_f) {
-        // The two kernels are independent (they only meet in loss_finish through an atomic ticket), so the second one is
-        // a programmatic dependent launch: its CTAs become resident as the first kernel's CTAs retire instead of waiting
-        // for the whole grid, which hides the launch gap and the tail of the first kernel.
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid_f); cfg.blockDim = dim3(kLossThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = grid_r ? 1 : 0;
-        DH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flat_kernel, pf, fin));
-    }
+    const int n_items = fp.n_flat_items + fp.n_small_items;
+    int grid_x = lc.sms * lc.occ[vi];
+    if (grid_x > n_items) grid_x = n_items;
+    kernel<<<grid_x, kLossThreads, smem, st>>>(fp);
+    DH_LAUNCH_CHECK();
     return DH_OK;
 }
 

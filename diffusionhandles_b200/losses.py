@@ -139,7 +139,7 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
             layers[i].resize_tables = N.ptr(t) if t is not None else None
         ws_fn = lib.dh_guidance_loss_patch_workspace_bytes if general else lib.dh_guidance_loss_workspace_bytes
         ws_bytes = int(ws_fn(L, max(sh[0] for sh in shapes)))
-        runner = (layers, torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes, tabs)
+        runner = (layers, torch.zeros(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes, tabs)   # zero once: the kernel re-arms its queue counters
         plan._runners[key] = runner
     layers, ws, ws_bytes, _ = runner
     grads: List[Optional[torch.Tensor]] = []

@@ -250,7 +250,9 @@ size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels);
  * contains every pair cell.  box_cells sizes the shared-memory buffers of the resized layers (0 = assume the whole grid);
  * plan_flags bit 0 = every background multiplicity is 0 or 1 (selects the bit-mask instantiation; 0 is always safe). */
 int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags);
-/* n_* are the list lengths the plan was built from (they are the means' denominators). */
+/* n_* are the list lengths the plan was built from (they are the means' denominators).  ONE persistent launch for all
+ * layers.  `ws` must be zero-filled once before its first use; the launch leaves its queue counters zeroed again, so the
+ * same workspace serves every following evaluation without a memset (one evaluation at a time per workspace). */
 int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan,
                      int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int box_cells, int plan_flags,
                      int fg_kind, int bg_kind,
