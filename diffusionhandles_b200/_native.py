@@ -94,9 +94,9 @@ _SIGNATURES = {
     "dh_loss_plan_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dh_build_loss_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
-    "dh_loss_plan_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
+    "dh_loss_plan_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+                                 c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "dh_scale_inplace_many": (c_int, [C.POINTER(c_void_p), C.POINTER(c_size_t), c_int, c_void_p, c_void_p]),
     "dh_raster_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
     {   // slice widths (longest row of the slice) and their exclusive scan
         int w = 0;
         if (tid < n_slices)
-            for (int r = tid * 32; r < min(n_rows, tid * 32 + 32); ++r) w = max(w, ucount[order[r]]);
+            for (int r = tid * 32; r < min(n_rows, tid * 32 + 32); ++r) w = max(w, (ucount[order[r]] + 3) & ~3);   // rows are padded to 4
         run = block_exclusive_scan(w, scan_smem, total);
         if (tid < n_slices) { soff[tid] = run; pv.ell_off[tid] = run; }
         if (tid == 0) { soff[n_slices] = total; pv.ell_off[n_slices] = total; }
@@ -218,6 +218,12 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
             const uint2 e = pv.pairs[base + k];
             dst[(size_t)k * 32] = (e.x & 0xFFFFu) | (e.y << 12);
             dst_box[(size_t)k * 32] = (uint32_t)to_box((int)(e.x & 0xFFFFu)) | (e.y << 12);
+        }
+        // every row is padded to a multiple of four entries with (first source, multiplicity 0): the kernel walks whole
+        // groups of four without per-entry predicates
+        for (int k = len; k < ((len + 3) & ~3); ++k) {
+            dst[(size_t)k * 32] = dst[0] & 0xFFFu;
+            dst_box[(size_t)k * 32] = dst_box[0] & 0xFFFu;
         }
     }
     if (tid == 0) {
@@ -271,13 +277,13 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int kLossThreads = 256;
 constexpr int kLossWarps = kLossThreads / 32;
-constexpr int kCtasPerSm = 3;                    // 80 registers per thread; ~64 KB of shared memory per CTA at config-3 sizes
+constexpr int kMaxGroups = 3;                    // groups of kLossThreads threads per CTA (one CTA per SM): 80 registers per thread
 constexpr int kPlaneCap = kMaxG * kMaxG;         // floats per tensor in the stage
 constexpr int kStageFloats = 2 * kPlaneCap;      // [cur planes][orig planes] = 32 KB
 constexpr int kOwnGroups = kPlaneCap / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
 constexpr int kRowUnroll = 4;    // independent gathers in flight per thread in the row walk
 constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): 2 * G / h <= 16 for h >= 8
-constexpr int kMaxPlanesPerItem = 8;
+constexpr int kMaxPlanesPerItem = 2;     // resized layers: one pair of planes per item (short items balance better)
 
 struct ResizeLayout {   // float offsets into the scratch area
     int tab, wrow, wcol, uc, uo, cnt, tmp, flat_cnt, total;
@@ -310,19 +316,19 @@ struct FusedParams {
     float* loss_out;
     ResizeLayout lay;
     int scratch_floats;
+    int ell_floats, ell_desc_at, ell_ent_at, ell_ent_cap;    // shared-memory copy of the sliced-ELL plan (0 = read it from global)
+    unsigned long long* debug;     // optional (DH_LOSS_DEBUG_BUF): per CTA {start ns, end ns, items, sm id}
 };
 
 struct WorkItem {
     int layer, c0, planes;
 };
 
-// Items of the two kinds are interleaved in proportion (Bresenham), so that HBM-heavy 64x64 planes and the
-// arithmetic-heavy resized planes are in flight together from the first to the last item.
+// Longest items first: the plane pairs of the resized layers (arithmetic heavy), then the 64x64 planes - the tail of the
+// launch is then made of the shortest items.
 __device__ __forceinline__ WorkItem decode_item(const FusedParams& p, int item) {
-    const int nf = p.n_flat_items, n = nf + p.n_small_items;
-    const int f0 = (int)((unsigned)item * (unsigned)nf / (unsigned)n), f1 = (int)((unsigned)(item + 1) * (unsigned)nf / (unsigned)n);
-    const int flat = f1 > f0;
-    const int idx = flat ? f0 : item - f0;
+    const int flat = item >= p.n_small_items;
+    const int idx = flat ? item - p.n_small_items : item;
     int l = -1;
 #pragma unroll
     for (int i = 0; i < kMaxLossLayers; ++i)
@@ -334,15 +340,15 @@ __device__ __forceinline__ WorkItem decode_item(const FusedParams& p, int item) 
     return w;
 }
 
-__device__ __forceinline__ float block_sum1(float v, float* sm) {
+__device__ __forceinline__ float block_sum1(float v, float* sm) {      // over the first kLossThreads threads of the CTA
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     if (lane_id() == 0) sm[warp_id()] = v;
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
     float t = lane_id() < kLossWarps ? sm[lane_id()] : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
     return t;
 }
 
@@ -350,10 +356,10 @@ __device__ __forceinline__ float block_sum1(float v, float* sm) {
 // fixed order -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l, and re-arms the counters.
 __device__ void loss_finish(const FusedParams& p, float* red32, unsigned int* ticket) {
     __threadfence();
-    __syncthreads();
+    __syncthreads();                      // every group of the CTA is done
     if (threadIdx.x == 0) *ticket = atomicAdd(p.counters + 1, 1u);
     __syncthreads();
-    if (*ticket != gridDim.x - 1) return;
+    if (*ticket != gridDim.x - 1 || threadIdx.x >= kLossThreads) return;
     __threadfence();
     float total = 0.0f;
     for (int l = 0; l < p.n_layers; ++l) {
@@ -373,7 +379,7 @@ __device__ void loss_finish(const FusedParams& p, float* red32, unsigned int* ti
     }
     if (threadIdx.x == 0) {
         p.loss_out[0] = total;
-        p.counters[0] = 0u;       // every CTA has drawn its last item: the queue can be re-armed for the next launch
+        p.counters[0] = 0u;       // every group has drawn its last item: the queue can be re-armed for the next launch
         p.counters[1] = 0u;
     }
 }
@@ -407,6 +413,7 @@ struct LayerTabSmall : LayerTabHead {
 struct LayerTab : LayerTabSmall {
     float wo[kMaxNative * kMaxNative], wt[kMaxNative * kMaxNative];
 };
+static_assert(kRowUnroll == 4, "the plan pads rows to four entries");
 static_assert(sizeof(LayerTabHead) % 16 == 0 && sizeof(LayerTabSmall) % 16 == 0 && sizeof(LayerTab) % 16 == 0, "tables are copied with 128-bit accesses");
 
 struct SetupParams {
@@ -497,8 +504,10 @@ struct FusedShared {
 
 // sum over the CTA of kN values per thread, results in every thread; fixed order (warp tree, then a tree over the warp
 // partials that every warp evaluates identically) -> deterministic.  One barrier.
+__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kLossThreads) : "memory"); }
+
 template <int kN>
-__device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8]) {
+__device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8], int gid) {
     static_assert(kN <= 8, "red holds 8 values per warp");
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -506,8 +515,8 @@ __device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8]) {
         for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
     if (lane_id() == 0)
 #pragma unroll
-        for (int i = 0; i < kN; ++i) red[warp_id()][i] = v[i];
-    __syncthreads();
+        for (int i = 0; i < kN; ++i) red[warp_id() & (kLossWarps - 1)][i] = v[i];
+    group_sync(gid);
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = red[lane_id() & (kLossWarps - 1)][i];
 #pragma unroll
@@ -527,14 +536,24 @@ __device__ __forceinline__ void pair_term(float fm, float d, float& acc, float& 
 
 // kG = 64: the loss grid of the reference; kG = 0: any grid <= 64.
 // kBinary: every background multiplicity is 0 or 1 (lists from np.nonzero) -> register bit masks for the own cells.
-template <int kG, bool kBinary, int kCtas>
-__global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const __grid_constant__ FusedParams p) {
+// One CTA per SM, made of up to kMaxGroups independent GROUPS of 256 threads.  A group is what a small CTA would be - its own
+// stage, scratch area, mbarrier and named barrier - but all groups of the SM share one copy of the sliced-ELL plan in shared
+// memory (the pair entries are re-read for every plane; from L1 / L2 they were the dominant stall).
+// kG = 64: the loss grid of the reference; kG = 0: any grid <= 64.
+// kBinary: every background multiplicity is 0 or 1 (lists from np.nonzero) -> register bit masks for the own cells.
+template <int kG, bool kBinary>
+__global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) float fsm[];
-    __shared__ __align__(16) FusedShared sh;
-    float* const st_cur = fsm;                        // the stage: [cur planes][orig planes]
-    float* const st_org = fsm + kPlaneCap;
-    float* const scratch = fsm + kStageFloats;
-    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    __shared__ __align__(16) FusedShared shg[kMaxGroups];
+    const int gid = threadIdx.x / kLossThreads, tid = threadIdx.x % kLossThreads, lane = lane_id(), wid = tid >> 5;
+    FusedShared& sh = shg[gid];
+#ifdef DH_LOSS_PHASE_TIMERS
+    const long long dbg_clock0 = clock64();
+#endif
+    float* const gbase = fsm + p.ell_floats + (size_t)gid * (kStageFloats + p.scratch_floats);
+    float* const st_cur = gbase;                      // the stage: [cur planes][orig planes]
+    float* const st_org = gbase + kPlaneCap;
+    float* const scratch = gbase + kStageFloats;
     const int n_items = p.n_flat_items + p.n_small_items;
 
     // Thread 0 is also the producer: it draws the next item from the queue while the current one is processed and, as soon
@@ -565,7 +584,23 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
     const PlanView& pv = p.pv;
     const int n_slices = p.fg_kind ? pv.hdr->n_slices : 0;
     const int n_rounds = (n_slices + kLossWarps - 1) / kLossWarps;
-    const int32_t* __restrict__ ell_off = pv.ell_off;
+    // the sliced-ELL plan: one copy in shared memory for all groups when it fits (ell_floats != 0), else read through L1
+    const int32_t* ell_off = pv.ell_off;
+    const uint32_t* row_desc = pv.row_desc;
+    const uint32_t* ent = pv.ent;
+    if (p.ell_floats) {
+        const int n_groups32 = p.fg_kind ? pv.hdr->n_groups * 32 : 0;
+        int32_t* s_off = reinterpret_cast<int32_t*>(fsm);
+        uint32_t* s_desc = reinterpret_cast<uint32_t*>(fsm) + p.ell_desc_at;
+        uint32_t* s_ent = reinterpret_cast<uint32_t*>(fsm) + p.ell_ent_at;
+        if (n_groups32 <= p.ell_ent_cap) {
+            for (int i = threadIdx.x; i <= n_slices; i += blockDim.x) s_off[i] = pv.ell_off[i];
+            for (int i = threadIdx.x; i < n_slices * 32; i += blockDim.x) s_desc[i] = pv.row_desc[i];
+            for (int i = threadIdx.x; i < n_groups32 / 4; i += blockDim.x)
+                reinterpret_cast<uint4*>(s_ent)[i] = reinterpret_cast<const uint4*>(pv.ent)[i];
+            ell_off = s_off; row_desc = s_desc; ent = s_ent;
+        }
+    }
     // membership of the own cells (flat layers) in the three background lists and in the set of destination rows, as
     // 16-bit masks (bit 4k+i = cell i of group k), precomputed by the plan.  Lists that come from np.nonzero never repeat a
     // cell; if a generic caller does, the multiplicities are re-read from the plan in the (slower) general path.
@@ -610,21 +645,30 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
     const int bw = any_box ? bs1 - bs0 + 1 : 0, bh = any_box ? br1 - br0 + 1 : 0;
     const int bcells = bw * bh;
     const bool box_overflow = bcells > lay.box_cap;   // the caller under-sized the box-local buffers: poison, never corrupt
-    // the plan's box-local cell ids are valid when the active box is the plan's box; 'local_avg' works on the whole grid,
-    // where box-local ids are plain cell ids
-    const bool whole_grid = bw == G && bh == G;
-    const uint32_t* __restrict__ s_desc = whole_grid ? pv.row_desc : pv.row_desc_box;
-    const uint32_t* __restrict__ s_ent = whole_grid ? pv.ent : pv.ent_box;
+    const int boff = br0 * bw + bs0;
+    auto to_box = [&](int cell) { const int r = kG ? cell >> 6 : cell / G; return r * bw + (cell - r * G) - boff; };
     __syncthreads();
 
     int cur_layer = -1;          // resized layer whose tables are in shared memory
     uint32_t phase = 0;
+    unsigned long long dbg_t0 = 0, dbg_items = 0;
+    if (p.debug && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
+#ifdef DH_LOSS_PHASE_TIMERS
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_t = dbg_clock0;
+    { const long long t_ = clock64(); ph[6] = t_ - ph_t; ph_t = t_; }
+#define DH_PH(i) { const long long t_ = clock64(); ph[i] += t_ - ph_t; ph_t = t_; }
+#else
+#define DH_PH(i)
+#endif
     for (;;) {
         int next_item = 0;
         if (tid == 0) next_item = (int)atomicAdd(p.counters, 1u);     // (its latency hides behind this item's work)
+        DH_PH(7)
         mbar_wait(&sh.full, phase);
+        DH_PH(0)
         phase ^= 1;
         if (sh.item >= n_items) break;
+        ++dbg_items;
         const int l = sh.layer, c0 = sh.c0, planes = sh.planes;
         const FusedLayer& L = p.lv[l];
         const float fscale = sh.lconst[l][0], lscale = sh.lconst[l][1], gscale = sh.lconst[l][2];
@@ -667,21 +711,22 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                 }
             }
             // the scratch area may still be read by slow warps (sign counts of the previous plane, a resized plane's buffers)
-            __syncthreads();
+            group_sync(gid);
+            DH_PH(1)
             // Destination rows: one thread per destination cell, its sources from the sliced-ELL plan
             for (int rd = 0; rd < n_rounds; ++rd) {
                 const int sl = slice_of(rd, wid);
                 if (sl >= n_slices) break;
-                const uint32_t desc = __ldg(pv.row_desc + sl * 32 + lane);
+                const uint32_t desc = row_desc[sl * 32 + lane];
                 const int len = (int)(desc >> 16), dcell = (int)(desc & 0xFFFFu);
-                const uint32_t* __restrict__ e_ptr = pv.ent + (size_t)__ldg(ell_off + sl) * 32 + lane;
+                const uint32_t* e_ptr = ent + ell_off[sl] * 32 + lane;
                 const float cval = st_cur[dcell];
                 float cn = 0.0f;
                 for (int k = 0; k < len; k += kRowUnroll) {
                     uint32_t e[kRowUnroll];
                     float o[kRowUnroll];
 #pragma unroll
-                    for (int u = 0; u < kRowUnroll; ++u) e[u] = k + u < len ? __ldg(e_ptr + (k + u) * 32) : 0u;
+                    for (int u = 0; u < kRowUnroll; ++u) e[u] = e_ptr[(k + u) * 32];      // (rows are padded to a multiple of kRowUnroll)
 #pragma unroll
                     for (int u = 0; u < kRowUnroll; ++u) o[u] = st_org[e[u] & 0xFFFu];
 #pragma unroll
@@ -689,7 +734,9 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                 }
                 if (len) cntb[dcell] = cn;
             }
-            block_sum<3>(sums, sh.red);       // (its barrier also orders the count stores and ends the reads of the stage)
+            DH_PH(2)
+            block_sum<3>(sums, sh.red, gid);       // (its barrier also orders the count stores and ends the reads of the stage)
+            DH_PH(3)
             if (tid == 0) stage_item(next_item);
             float bg_term = 0.0f, bscale = 0.0f;
             if (p.bg_kind == 1) {
@@ -727,6 +774,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                     st_cs_f4(g + q, make_float4(v[0], v[1], v[2], v[3]));
                 }
             }
+            DH_PH(4)
         } else {
             // ------------------------------------------------------------------ planes of a layer below the loss grid
             const int h = L.h, w = L.w, hw = h * w;
@@ -734,7 +782,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
             const float* __restrict__ gwo = tl->wo;      // up^T(background multiplicities), read through L1
             const float* __restrict__ gwt = tl->wt;
             if (l != cur_layer) {       // (a CTA crosses a layer boundary a handful of times)
-                __syncthreads();        // slow warps may still read the previous layer's tables
+                group_sync(gid);        // slow warps may still read the previous layer's tables
                 const float4* src = reinterpret_cast<const float4*>(static_cast<const LayerTabHead*>(tl));
                 float4* dst = reinterpret_cast<float4*>(&T);
                 for (int i = tid; i < (int)(sizeof(LayerTabHead) / 16); i += kLossThreads) dst[i] = src[i];
@@ -751,7 +799,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                 const float* const pc1 = two ? pc0 + hw : pc0;
                 const float* const po1 = two ? po0 + hw : po0;
                 const bool last_pair = pl + 2 >= planes;
-                __syncthreads();          // tables loaded; scratch of the previous pair / flat item no longer read
+                group_sync(gid);          // tables loaded; scratch of the previous pair / flat item no longer read
                 if (box_overflow) {
                     if (tid == 0) {
                         for (int j = 0; j < (two ? 2 : 1); ++j) {
@@ -780,23 +828,23 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                                              hy * (hx * po1[i00] + lx * po1[i01]) + ly * (hx * po1[i10] + lx * po1[i11]));
                     }
                 }
-                __syncthreads();
+                group_sync(gid);
                 float sums[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // per plane: foreground sum, two background sums
                 for (int rd = 0; rd < n_rounds; ++rd) {
                     const int sl = slice_of(rd, wid);
                     if (sl >= n_slices) break;
-                    const uint32_t desc = __ldg(s_desc + sl * 32 + lane);
-                    const int len = (int)(desc >> 16), db = (int)(desc & 0xFFFFu);
-                    const uint32_t* __restrict__ e_ptr = s_ent + (size_t)__ldg(ell_off + sl) * 32 + lane;
+                    const uint32_t desc = row_desc[sl * 32 + lane];
+                    const int len = (int)(desc >> 16), db = len ? to_box((int)(desc & 0xFFFFu)) : 0;
+                    const uint32_t* e_ptr = ent + ell_off[sl] * 32 + lane;
                     const float2 cval = suc[db];
                     float cn0 = 0.0f, cn1 = 0.0f;
                     for (int k = 0; k < len; k += kRowUnroll) {
                         uint32_t e[kRowUnroll];
                         float2 o[kRowUnroll];
 #pragma unroll
-                        for (int u = 0; u < kRowUnroll; ++u) e[u] = k + u < len ? __ldg(e_ptr + (k + u) * 32) : 0u;
+                        for (int u = 0; u < kRowUnroll; ++u) e[u] = e_ptr[(k + u) * 32];      // (rows are padded to a multiple of kRowUnroll)
 #pragma unroll
-                        for (int u = 0; u < kRowUnroll; ++u) o[u] = suo[e[u] & 0xFFFu];
+                        for (int u = 0; u < kRowUnroll; ++u) o[u] = suo[to_box((int)(e[u] & 0xFFFu))];
 #pragma unroll
                         for (int u = 0; u < kRowUnroll; ++u) {
                             const float fm = (float)(e[u] >> 12);          // (m = 0 past the end of the row: no-op)
@@ -824,7 +872,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                         sums[4] = fmaf(mz, fabsf(uo.y - uc.y), sums[4]);
                     }
                 }
-                block_sum<6>(sums, sh.red);
+                block_sum<6>(sums, sh.red, gid);
                 if (last_pair && tid == 0) stage_item(next_item);      // every read of the staged planes is behind the barrier
                 float bscale0 = 0.0f, bscale1 = 0.0f;
                 {
@@ -854,7 +902,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                         }
                         gu[i] = v;
                     }
-                    __syncthreads();
+                    group_sync(gid);
                     for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
                         const int lo = T.ylo[yi];
                         const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
@@ -869,7 +917,7 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                             tmp[yi * G + s] = make_float2(a0, a1);
                         }
                     }
-                    __syncthreads();
+                    group_sync(gid);
                     for (int yi = wid; yi < h; yi += kLossWarps) {
                         const bool row_in = yi >= ny0 && yi <= ny1;
                         for (int xj = lane; xj < w; xj += 32) {
@@ -894,9 +942,22 @@ __global__ void __launch_bounds__(kLossThreads, kCtas) loss_fused_kernel(const _
                     }
                 }
             }
+            DH_PH(5)
         }
     }
-    loss_finish(p, sh.red32, &sh.ticket);
+    if (p.debug && tid == 0) {
+        unsigned long long t1;
+        unsigned int smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        const int slot = blockIdx.x * kMaxGroups + gid;
+        p.debug[4 * slot + 0] = dbg_t0; p.debug[4 * slot + 1] = t1;
+        p.debug[4 * slot + 2] = dbg_items; p.debug[4 * slot + 3] = smid;
+#ifdef DH_LOSS_PHASE_TIMERS
+        for (int i = 0; i < 8; ++i) p.debug[4 * 1024 + 8 * slot + i] = (unsigned long long)ph[i];
+#endif
+    }
+    loss_finish(p, shg[0].red32, &shg[0].ticket);
 }
 
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, size_t n, const float* __restrict__ scale) {
@@ -1000,18 +1061,20 @@ int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int
     return DH_OK;
 }
 
-int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags) {
+int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags, int* ell_slices, int* ell_groups) {
     DH_REQUIRE(plan_header_host);
     const PlanHeader* h = static_cast<const PlanHeader*>(plan_header_host);
     if (n_pairs) *n_pairs = h->n_pairs;
+    if (ell_slices) *ell_slices = h->n_slices;
+    if (ell_groups) *ell_groups = h->n_groups;
     if (plan_flags) *plan_flags = h->reserved & 1;
     if (box_cells) *box_cells = h->box_r1 >= h->box_r0 ? (h->box_r1 - h->box_r0 + 1) * (h->box_s1 - h->box_s0 + 1) : 0;
     return DH_OK;
 }
 
 int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan, int n_fg, int n_bg_orig,
-                     int n_bg_trans, int n_bg_common, int box_cells, int plan_flags, int fg_kind, int bg_kind, float* loss_out,
-                     void* ws, size_t ws_bytes, void* stream) {
+                     int n_bg_trans, int n_bg_common, int box_cells, int plan_flags, int ell_slices, int ell_groups, int fg_kind,
+                     int bg_kind, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
     DH_REQUIRE(layers_host && n_layers >= 1 && n_layers <= kMaxLossLayers && loss_out && ws && plan);
     DH_REQUIRE(grid >= 1 && grid <= kMaxG);
     DH_REQUIRE(n_fg >= 0 && n_bg_orig >= 0 && n_bg_trans >= 0 && n_bg_common >= 0);
@@ -1060,7 +1123,6 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
             if (s.w * wmax > wcol_floats) wcol_floats = s.w * wmax;
         }
     }
-    if (fp.n_flat_items + fp.n_small_items > 46000) return DH_ERR_UNSUPPORTED;      // 32-bit item interleave arithmetic
     fp.n_layers = n_layers;
     fp.G = grid;
     size_t o_counter;
@@ -1072,6 +1134,10 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     fp.partial = static_cast<float*>(ws);
     fp.counters = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
     fp.loss_out = loss_out;
+    {
+        const char* e = getenv("DH_LOSS_DEBUG_BUF");      // developer aid: address of a device buffer of 4 * grid u64
+        fp.debug = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    }
     // scratch: the tables of the current resized layer, then the per-plane buffers of a resized plane overlaid with the
     // sign-count buffer of a flat plane
     auto up4 = [](int v) { return (v + 3) / 4 * 4; };
@@ -1093,46 +1159,61 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     if (fp.n_flat_items && lay.flat_cnt + GG > o) o = lay.flat_cnt + GG;
     lay.total = o;
     fp.scratch_floats = up4(o);
-    const size_t smem = sizeof(float) * ((size_t)kStageFloats + fp.scratch_floats);
     cudaStream_t st = as_stream(stream);
     // per-process caches of the launch geometry queries (this entry point runs every denoising step)
     struct LaunchCache {
-        int sms;
-        size_t smem_attr_set[8];
-        int occ[8];
-        size_t occ_smem[8];
+        int sms, max_smem;
+        size_t smem_attr_set[4];
     };
     static LaunchCache caches[64];          // zero-initialised; one entry per device (function attributes are per device)
     int dev = 0;
     DH_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DH_ERR_UNSUPPORTED;
     LaunchCache& lc = caches[dev];
-    if (!lc.sms) DH_CUDA_CHECK(cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev));
-    // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
-    static int ctas_env = -1;
-    if (ctas_env < 0) {
-        const char* e = getenv("DH_LOSS_CTAS");
-        ctas_env = e && atoi(e) == 4 ? 4 : kCtasPerSm;
+    if (!lc.sms) {
+        DH_CUDA_CHECK(cudaDeviceGetAttribute(&lc.sms, cudaDevAttrMultiProcessorCount, dev));
+        DH_CUDA_CHECK(cudaDeviceGetAttribute(&lc.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     }
-    const int vi = (grid == 64 ? 2 : 0) + ((plan_flags & 1) ? 1 : 0) + (ctas_env == 3 ? 4 : 0);   // bit 2: three CTAs per SM
-    void (*kernel)(const FusedParams) =
-        vi == 3 ? loss_fused_kernel<64, true, 4> : vi == 2 ? loss_fused_kernel<64, false, 4> : vi == 1 ? loss_fused_kernel<0, true, 4>
-        : vi == 0 ? loss_fused_kernel<0, false, 4> : vi == 7 ? loss_fused_kernel<64, true, 3> : vi == 6 ? loss_fused_kernel<64, false, 3>
-        : vi == 5 ? loss_fused_kernel<0, true, 3> : loss_fused_kernel<0, false, 3>;
+    // shared memory: [one copy of the sliced-ELL plan][per group: stage + scratch]; as many groups (<= 3) as fit, the plan copy
+    // is dropped (entries then come through L1) before the group count goes below two
+    const size_t group_bytes = sizeof(float) * ((size_t)kStageFloats + fp.scratch_floats);
+    const size_t static_bytes = 2048;       // FusedShared x kMaxGroups and the driver's reservation, rounded up
+    const size_t budget = (size_t)lc.max_smem > static_bytes ? (size_t)lc.max_smem - static_bytes : 0;
+    int ell_words = 0;
+    if (fg_kind && ell_slices > 0 && ell_groups > 0) {
+        fp.ell_desc_at = up4(ell_slices + 1);
+        fp.ell_ent_at = fp.ell_desc_at + ell_slices * 32;
+        fp.ell_ent_cap = ell_groups * 32;
+        ell_words = up4(fp.ell_ent_at + fp.ell_ent_cap);
+        ell_words = (ell_words + 31) / 32 * 32;        // the groups' stages stay 128-byte aligned
+    }
+    int groups = 0;
+    if (ell_words && sizeof(float) * ell_words + 2 * group_bytes <= budget) {
+        groups = sizeof(float) * ell_words + 3 * group_bytes <= budget ? 3 : 2;
+        fp.ell_floats = ell_words;
+    } else {
+        fp.ell_floats = 0;
+        for (groups = kMaxGroups; groups > 1 && groups * group_bytes > budget; --groups) {}
+    }
+    const int n_items = fp.n_flat_items + fp.n_small_items;
+    {
+        const char* e = getenv("DH_LOSS_GROUPS");       // developer knob
+        if (e && atoi(e) >= 1 && atoi(e) < groups) groups = atoi(e);
+    }
+    while (groups > 1 && lc.sms * (groups - 1) >= n_items) --groups;      // tiny problems: no idle groups
+    const size_t smem = sizeof(float) * fp.ell_floats + groups * group_bytes;
+    if (smem > budget + static_bytes) return DH_ERR_UNSUPPORTED;
+    // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
+    const int vi = (grid == 64 ? 2 : 0) + ((plan_flags & 1) ? 1 : 0);
+    void (*kernel)(const FusedParams) = vi == 3 ? loss_fused_kernel<64, true> : vi == 2 ? loss_fused_kernel<64, false>
+                                        : vi == 1 ? loss_fused_kernel<0, true> : loss_fused_kernel<0, false>;
     if (smem > lc.smem_attr_set[vi]) {
         DH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lc.smem_attr_set[vi] = smem;
     }
-    if (!lc.occ[vi] || lc.occ_smem[vi] != smem) {
-        int per_sm = 1;
-        DH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLossThreads, smem));
-        lc.occ[vi] = per_sm < 1 ? 1 : per_sm;
-        lc.occ_smem[vi] = smem;
-    }
-    const int n_items = fp.n_flat_items + fp.n_small_items;
-    int grid_x = lc.sms * lc.occ[vi];
-    if (grid_x > n_items) grid_x = n_items;
-    kernel<<<grid_x, kLossThreads, smem, st>>>(fp);
+    int grid_x = lc.sms;
+    if (grid_x * groups > n_items) grid_x = (n_items + groups - 1) / groups;
+    kernel<<<grid_x, kLossThreads * groups, smem, st>>>(fp);
     DH_LAUNCH_CHECK();
     return DH_OK;
 }

@@ -19,7 +19,8 @@ def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, s
                    fg_weight: float = 1.5, bg_weight: float = 1.25, num_optsteps: int = 3, guidance_max_step: int = 38,
                    guidance_schedule_type: str = "constant", bg_loss_type: str = "global_avg", fg_patch_size: int = 1,
                    bg_patch_size: int = 1, step_size: float = 0.1, scale_model_input: Optional[Callable] = None,
-                   cfg_noise: Optional[Callable] = None, skip_zero_weight_layers: bool = False) -> torch.Tensor:
+                   cfg_noise: Optional[Callable] = None, skip_zero_weight_layers: bool = False,
+                   on_step: Optional[Callable] = None) -> torch.Tensor:
     """latents (1,4,h,w).  ``unet(latents_in, t) -> (noise_pred, [act0, act1, act2])`` with activations (1,C,h,w) that are
     differentiable w.r.t. ``latents_in``; ``scheduler_step(noise_pred, t, latents) -> latents``;
     ``cfg_noise(latents, t, t_idx) -> noise_pred`` runs the classifier-free-guidance forward (defaults to ``unet``).
@@ -49,7 +50,11 @@ def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, s
                     grad = torch.autograd.grad(loss, [lat])[0]
                     latents = lat.detach() - grad * step_size
             iteration += 1
+        if on_step is not None:
+            on_step('opt', latents)
         with torch.no_grad():
             noise_pred = cfg_noise(latents, t, t_idx) if cfg_noise is not None else unet(latents, t)[0]
             latents = scheduler_step(noise_pred, t, latents)
+            if on_step is not None:
+                on_step('post-opt', latents)
     return latents

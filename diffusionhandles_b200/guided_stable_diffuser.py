@@ -138,15 +138,124 @@ def make_guidance_weight_schedule(fg_weight: float, bg_weight: float, guidance_m
 
 
 class GuidedStableDiffuser:
-    """Carrier of the two hot-path methods of the reference class (same names / signatures)."""
+    """The reference class's hot-path methods under their own names and signatures.  The diffusion models themselves
+    (U-Net with recorded activations, VAE, CLIP tokenizer / text encoder, DDIM scheduler) are stock PyTorch / diffusers
+    objects outside this build: pass them in (``unet=..., scheduler=..., vae=..., tokenizer=..., text_encoder=...``) and
+    ``guided_inference`` runs the reference's guided denoising loop with the fused sm_100a loss kernel in it."""
 
-    def __init__(self, conf=None):
+    def __init__(self, conf=None, unet=None, scheduler=None, vae=None, tokenizer=None, text_encoder=None):
         self.conf = conf
+        self.unet, self.scheduler, self.vae, self.tokenizer, self.text_encoder = unet, scheduler, vae, tokenizer, text_encoder
         self.device = torch.device("cpu")
 
     def to(self, device: torch.device = None):
+        for m in (self.unet, self.vae, self.text_encoder):
+            if m is not None and hasattr(m, "to"):
+                m.to(device=device)
         self.device = device
         return self
+
+    def _conf(self, name, default):
+        return getattr(self.conf, name, default) if self.conf is not None else default
+
+    def get_feature_shape(self):
+        """guided_stable_diffuser.py:104-109: latent grid of the injected U-Net (64 x 64 x 4 for SD2-depth)."""
+        cfg = getattr(self.unet, "config", None)
+        n = int(getattr(cfg, "sample_size", LATENT_GRID)) if cfg is not None else LATENT_GRID
+        return [n, n, 4]
+
+    def init_depth(self, depth):
+        """guided_stable_diffuser.py:111-127: bicubic resize to the latent grid, then min/max normalisation to [-1, 1]."""
+        h, w = self.get_feature_shape()[:2]
+        depth = torch.nn.functional.interpolate(depth, size=(h, w), mode="bicubic", align_corners=False)
+        lo = torch.amin(depth, dim=[1, 2, 3], keepdim=True)
+        hi = torch.amax(depth, dim=[1, 2, 3], keepdim=True)
+        return 2.0 * (depth - lo) / (hi - lo) - 1.0
+
+    def get_timesteps(self, num_inference_steps, strength):
+        """guided_stable_diffuser.py:586-593."""
+        init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
+        t_start = max(num_inference_steps - init_timestep, 0)
+        return self.scheduler.timesteps[t_start * getattr(self.scheduler, "order", 1):], num_inference_steps - t_start
+
+    def guided_inference(self, latents: torch.Tensor, depth: torch.Tensor, uncond_embeddings: torch.Tensor, prompt: str,
+                         activations_orig, correspondences: torch.Tensor, fg_weight: float = None, bg_weight: float = None,
+                         save_denoising_steps: bool = False):
+        """guided_stable_diffuser.py:291-488, same signature.  Per denoising step up to ``num_optsteps`` gradient steps on
+        the latents driven by sum_l fgw[l] L_fg,l + bgw[l] L_bg,l (ONE fused K4 launch per evaluation, :415-434), then the
+        classifier-free-guidance forward (scale 7.5, :452-470) and the scheduler step; finally the VAE decode.  Needs the
+        injected diffusion models; without them this raises NotImplementedError (they are outside this build)."""
+        import inspect
+        from .guided_loop import guided_denoise
+        missing = [n for n in ("unet", "scheduler") if getattr(self, n) is None]
+        if missing:
+            raise NotImplementedError(f"guided_inference needs the stock diffusion models ({', '.join(missing)}); pass them to "
+                                      "GuidedStableDiffuser(conf, unet=..., scheduler=..., vae=..., tokenizer=..., text_encoder=...)")
+        fg_weight = self._conf("fg_weight", 1.5) if fg_weight is None else fg_weight
+        bg_weight = self._conf("bg_weight", 1.25) if bg_weight is None else bg_weight
+        use_depth = self._conf("use_depth", True)
+        with torch.no_grad():
+            generator = torch.manual_seed(self._conf("seed", 2773))
+            n_steps = self._conf("num_timesteps", 50)
+            self.scheduler.set_timesteps(n_steps, device=self.device)
+            timesteps, _ = self.get_timesteps(n_steps, 1.0)
+            pc = self.process_correspondences(correspondences, img_res=depth.shape[-1], bg_erosion=self._conf("bg_erosion", 0))
+            if use_depth:
+                depth = self.init_depth(depth)
+            if self.tokenizer is not None and self.text_encoder is not None:
+                ids = self.tokenizer([prompt], padding="max_length", truncation=True, max_length=self.tokenizer.model_max_length,
+                                     return_tensors="pt")
+                cond = self.text_encoder(ids.input_ids.to(self.device))[0]
+            else:                                # a pre-computed prompt embedding may be passed instead of a string
+                cond = prompt
+            step_params = set(inspect.signature(self.scheduler.step).parameters.keys())
+            extra = {}
+            if "eta" in step_params:
+                extra["eta"] = 0.0
+            if "generator" in step_params:
+                extra["generator"] = generator
+
+        def unet_fn(model_in, t):
+            if use_depth:
+                model_in = torch.cat([model_in, depth], dim=1)
+            out = self.unet(model_in, t, encoder_hidden_states=cond, cross_attention_kwargs=None, return_dict=False)
+            return out[0], [out[4], out[5], out[6]]
+
+        def cfg_noise(lat, t, t_idx):
+            model_in = self.scheduler.scale_model_input(torch.cat([lat] * 2), t)
+            if use_depth:
+                model_in = torch.cat([model_in, torch.cat([depth] * 2, dim=0)], dim=1)
+            emb = torch.cat([uncond_embeddings[t_idx].expand(*cond.shape), cond])
+            noise = self.unet(model_in, t, encoder_hidden_states=emb, cross_attention_kwargs=None, return_dict=False)[0]
+            n_uncond, n_text = noise.chunk(2)
+            return n_uncond + 7.5 * (n_text - n_uncond)
+
+        steps = {'opt': [], 'post-opt': []} if save_denoising_steps else None
+
+        def on_step(kind, lat):
+            if steps is not None:
+                if kind == 'opt':
+                    steps['opt'].append([self.decode_latent_image(lat.detach()).cpu()])
+                else:
+                    steps['opt'][-1].append(self.decode_latent_image(lat.detach()).cpu())
+
+        latents = guided_denoise(
+            latents, timesteps, unet_fn, lambda noise, t, lat: self.scheduler.step(noise, t, lat, **extra, return_dict=False)[0],
+            activations_orig, pc, fg_weight=fg_weight, bg_weight=bg_weight, num_optsteps=self._conf("num_optsteps", 3),
+            guidance_max_step=self._conf("guidance_max_step", 38), guidance_schedule_type=self._conf("guidance_schedule_type", "constant"),
+            bg_loss_type=self._conf("bg_loss_type", "global_avg"), fg_patch_size=self._conf("fg_patch_size", 1),
+            bg_patch_size=self._conf("bg_patch_size", 1), scale_model_input=self.scheduler.scale_model_input, cfg_noise=cfg_noise,
+            on_step=on_step if steps is not None else None)
+        with torch.no_grad():
+            image = self.decode_latent_image(latents)
+        return (image, steps) if save_denoising_steps else image
+
+    def decode_latent_image(self, latent_image: torch.Tensor) -> torch.Tensor:
+        """guided_stable_diffuser.py:285-288 (VAE decode + the [0,1] post-processing of diffusers' VaeImageProcessor)."""
+        if self.vae is None:
+            return latent_image
+        image = self.vae.decode(latent_image / self.vae.config.scaling_factor, return_dict=False)[0]
+        return (image / 2 + 0.5).clamp(0, 1)
 
     @staticmethod
     def get_depth_intrinsics(device: torch.device = None):

@@ -68,9 +68,11 @@ class LossPlan:
                                        N.stream_handle(torch.device(device))), "dh_build_loss_plan")
         # one small read-back per edit: the plan header tells how big the box-local buffers of the kernel must be
         hdr = self.buf[:64].cpu().numpy().tobytes()
-        n_pairs, box, flags = C.c_int(0), C.c_int(0), C.c_int(0)
-        N.check(lib.dh_loss_plan_info(hdr, C.byref(n_pairs), C.byref(box), C.byref(flags)), "dh_loss_plan_info")
+        n_pairs, box, flags, slices, groups = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        N.check(lib.dh_loss_plan_info(hdr, C.byref(n_pairs), C.byref(box), C.byref(flags), C.byref(slices), C.byref(groups)),
+                "dh_loss_plan_info")
         self.n_pairs, self.box_cells, self.flags = n_pairs.value, box.value, flags.value
+        self.ell_slices, self.ell_groups = slices.value, groups.value
         self._tables = {}
         self._runners = {}
 
@@ -159,7 +161,7 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
     st = N.stream_handle(dev)
     if not general:
         N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
-                                     fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
+                                     plan.ell_slices, plan.ell_groups, fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
     else:
         N.check(lib.dh_guidance_loss_patch(layers, L, plan.grid, patch, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind,
                                            out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss_patch")
