@@ -317,6 +317,7 @@ struct FusedParams {
     ResizeLayout lay;
     int scratch_floats;
     int ell_floats, ell_desc_at, ell_ent_at, ell_ent_cap;    // shared-memory copy of the sliced-ELL plan (0 = read it from global)
+    int ell_slices;     // slices of the plan as the caller read them from the plan header (0 = unknown: read the header)
     unsigned long long* debug;     // optional (DH_LOSS_DEBUG_BUF): per CTA {start ns, end ns, items, sm id}
 };
 
@@ -582,18 +583,18 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
 
     const int G = kG ? kG : p.G, GG = G * G;
     const PlanView& pv = p.pv;
-    const int n_slices = p.fg_kind ? pv.hdr->n_slices : 0;
+    const int n_slices = p.fg_kind ? (p.ell_slices ? p.ell_slices : pv.hdr->n_slices) : 0;
     const int n_rounds = (n_slices + kLossWarps - 1) / kLossWarps;
     // the sliced-ELL plan: one copy in shared memory for all groups when it fits (ell_floats != 0), else read through L1
     const int32_t* ell_off = pv.ell_off;
     const uint32_t* row_desc = pv.row_desc;
     const uint32_t* ent = pv.ent;
     if (p.ell_floats) {
-        const int n_groups32 = p.fg_kind ? pv.hdr->n_groups * 32 : 0;
+        const int n_groups32 = p.fg_kind ? p.ell_ent_cap : 0;       // (the caller's ell_groups * 32)
         int32_t* s_off = reinterpret_cast<int32_t*>(fsm);
         uint32_t* s_desc = reinterpret_cast<uint32_t*>(fsm) + p.ell_desc_at;
         uint32_t* s_ent = reinterpret_cast<uint32_t*>(fsm) + p.ell_ent_at;
-        if (n_groups32 <= p.ell_ent_cap) {
+        {
             for (int i = threadIdx.x; i <= n_slices; i += blockDim.x) s_off[i] = pv.ell_off[i];
             for (int i = threadIdx.x; i < n_slices * 32; i += blockDim.x) s_desc[i] = pv.row_desc[i];
             for (int i = threadIdx.x; i < n_groups32 / 4; i += blockDim.x)
@@ -646,6 +647,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
     const int bcells = bw * bh;
     const bool box_overflow = bcells > lay.box_cap;   // the caller under-sized the box-local buffers: poison, never corrupt
     const int boff = br0 * bw + bs0;
+    const unsigned bw_magic = bw > 1 ? (unsigned)((0x100000000ull + bw - 1) / bw) : 0xFFFFFFFFu;     // floor(i / bw) = umulhi(i, magic), i < 2^20
     auto to_box = [&](int cell) { const int r = kG ? cell >> 6 : cell / G; return r * bw + (cell - r * G) - boff; };
     __syncthreads();
 
@@ -663,7 +665,6 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
     for (;;) {
         int next_item = 0;
         if (tid == 0) next_item = (int)atomicAdd(p.counters, 1u);     // (its latency hides behind this item's work)
-        DH_PH(7)
         mbar_wait(&sh.full, phase);
         DH_PH(0)
         phase ^= 1;
@@ -712,7 +713,6 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
             }
             // the scratch area may still be read by slow warps (sign counts of the previous plane, a resized plane's buffers)
             group_sync(gid);
-            DH_PH(1)
             // Destination rows: one thread per destination cell, its sources from the sliced-ELL plan
             for (int rd = 0; rd < n_rounds; ++rd) {
                 const int sl = slice_of(rd, wid);
@@ -734,9 +734,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                 }
                 if (len) cntb[dcell] = cn;
             }
-            DH_PH(2)
             block_sum<3>(sums, sh.red, gid);       // (its barrier also orders the count stores and ends the reads of the stage)
-            DH_PH(3)
             if (tid == 0) stage_item(next_item);
             float bg_term = 0.0f, bscale = 0.0f;
             if (p.bg_kind == 1) {
@@ -774,7 +772,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                     st_cs_f4(g + q, make_float4(v[0], v[1], v[2], v[3]));
                 }
             }
-            DH_PH(4)
+            DH_PH(1)
         } else {
             // ------------------------------------------------------------------ planes of a layer below the loss grid
             const int h = L.h, w = L.w, hw = h * w;
@@ -814,21 +812,20 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                 const int ny0 = T.box[4], ny1 = T.box[5], nx0 = T.box[6], nx1 = T.box[7];
                 // up(cur), up(orig) inside the box (and the box-local sign counts start at zero)
                 for (int i = tid; i < bcells; i += kLossThreads) gu[i] = make_float2(0.0f, 0.0f);
-                for (int r = br0 + wid; r <= br1; r += kLossWarps) {
+                for (int b = tid; b < bcells; b += kLossThreads) {        // (flat over the box: every lane busy)
+                    const int rr = (int)__umulhi((unsigned)b, bw_magic), r = br0 + rr, s = bs0 + b - rr * bw;
                     const int y0 = T.ty0[r] * w, y1 = T.ty1[r] * w;
                     const float ly = T.tly[r], hy = 1.0f - ly;
-                    for (int s = bs0 + lane; s <= bs1; s += 32) {
-                        const int x0 = T.tx0[s], x1 = T.tx1[s];
-                        const float lx = T.tlx[s], hx = 1.0f - lx;
-                        const int b = (r - br0) * bw + (s - bs0);
-                        const int i00 = y0 + x0, i01 = y0 + x1, i10 = y1 + x0, i11 = y1 + x1;
-                        suc[b] = make_float2(hy * (hx * pc0[i00] + lx * pc0[i01]) + ly * (hx * pc0[i10] + lx * pc0[i11]),
-                                             hy * (hx * pc1[i00] + lx * pc1[i01]) + ly * (hx * pc1[i10] + lx * pc1[i11]));
-                        suo[b] = make_float2(hy * (hx * po0[i00] + lx * po0[i01]) + ly * (hx * po0[i10] + lx * po0[i11]),
-                                             hy * (hx * po1[i00] + lx * po1[i01]) + ly * (hx * po1[i10] + lx * po1[i11]));
-                    }
+                    const int x0 = T.tx0[s], x1 = T.tx1[s];
+                    const float lx = T.tlx[s], hx = 1.0f - lx;
+                    const int i00 = y0 + x0, i01 = y0 + x1, i10 = y1 + x0, i11 = y1 + x1;
+                    suc[b] = make_float2(hy * (hx * pc0[i00] + lx * pc0[i01]) + ly * (hx * pc0[i10] + lx * pc0[i11]),
+                                         hy * (hx * pc1[i00] + lx * pc1[i01]) + ly * (hx * pc1[i10] + lx * pc1[i11]));
+                    suo[b] = make_float2(hy * (hx * po0[i00] + lx * po0[i01]) + ly * (hx * po0[i10] + lx * po0[i11]),
+                                         hy * (hx * po1[i00] + lx * po1[i01]) + ly * (hx * po1[i10] + lx * po1[i11]));
                 }
                 group_sync(gid);
+                DH_PH(2)
                 float sums[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // per plane: foreground sum, two background sums
                 for (int rd = 0; rd < n_rounds; ++rd) {
                     const int sl = slice_of(rd, wid);
@@ -872,7 +869,9 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                         sums[4] = fmaf(mz, fabsf(uo.y - uc.y), sums[4]);
                     }
                 }
+                DH_PH(3)
                 block_sum<6>(sums, sh.red, gid);
+                DH_PH(4)
                 if (last_pair && tid == 0) stage_item(next_item);      // every read of the staged planes is behind the barrier
                 float bscale0 = 0.0f, bscale1 = 0.0f;
                 {
@@ -903,21 +902,21 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                         gu[i] = v;
                     }
                     group_sync(gid);
-                    for (int yi = ny0 + wid; yi <= ny1; yi += kLossWarps) {
+                    for (int i = tid; i < (ny1 - ny0 + 1) * bw; i += kLossThreads) {       // (flat over native rows x box columns)
+                        const int yr = (int)__umulhi((unsigned)i, bw_magic), yi = ny0 + yr, sc = i - yr * bw;
                         const int lo = T.ylo[yi];
                         const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
                         const float* wr = swrow + yi * win - lo;
-                        for (int s = bs0 + lane; s <= bs1; s += 32) {
-                            float a0 = 0.0f, a1 = 0.0f;
-                            const float2* gp = gu + (s - bs0) - br0 * bw;
-                            for (int r = ra; r <= rb; ++r) {
-                                const float2 gv = gp[r * bw];
-                                a0 = fmaf(wr[r], gv.x, a0); a1 = fmaf(wr[r], gv.y, a1);
-                            }
-                            tmp[yi * G + s] = make_float2(a0, a1);
+                        float a0 = 0.0f, a1 = 0.0f;
+                        const float2* gp = gu + sc - br0 * bw;
+                        for (int r = ra; r <= rb; ++r) {
+                            const float2 gv = gp[r * bw];
+                            a0 = fmaf(wr[r], gv.x, a0); a1 = fmaf(wr[r], gv.y, a1);
                         }
+                        tmp[yi * G + bs0 + sc] = make_float2(a0, a1);
                     }
                     group_sync(gid);
+                    DH_PH(5)
                     for (int yi = wid; yi < h; yi += kLossWarps) {
                         const bool row_in = yi >= ny0 && yi <= ny1;
                         for (int xj = lane; xj < w; xj += 32) {
@@ -942,7 +941,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                     }
                 }
             }
-            DH_PH(5)
+            DH_PH(7)
         }
     }
     if (p.debug && tid == 0) {
@@ -1184,6 +1183,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         fp.ell_desc_at = up4(ell_slices + 1);
         fp.ell_ent_at = fp.ell_desc_at + ell_slices * 32;
         fp.ell_ent_cap = ell_groups * 32;
+        fp.ell_slices = ell_slices;
         ell_words = up4(fp.ell_ent_at + fp.ell_ent_cap);
         ell_words = (ell_words + 31) / 32 * 32;        // the groups' stages stay 128-byte aligned
     }
