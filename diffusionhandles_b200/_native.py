@@ -41,6 +41,11 @@ class dh_loss_layer(C.Structure):
                 ("w", C.c_int32), ("fg_weight", c_float), ("bg_weight", c_float), ("resize_tables", c_void_p)]
 
 
+class dh_loss_plan_desc(C.Structure):
+    _fields_ = [("n_pairs", C.c_int32), ("box_cells", C.c_int32), ("flags", C.c_int32), ("ell_slices", C.c_int32),
+                ("ell_groups", C.c_int32), ("n_src_cells", C.c_int32)]
+
+
 _SIGNATURES = {
     "dh_status_string": (C.c_char_p, [c_int]),
     "dh_abi_version": (c_int, []),
@@ -94,8 +99,8 @@ _SIGNATURES = {
     "dh_loss_plan_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dh_build_loss_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
-    "dh_loss_plan_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
-    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+    "dh_loss_plan_info": (c_int, [c_void_p, C.POINTER(dh_loss_plan_desc)]),
+    "dh_guidance_loss": (c_int, [C.POINTER(dh_loss_layer), c_int, c_int, c_void_p, C.POINTER(dh_loss_plan_desc), c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "dh_scale_inplace_many": (c_int, [C.POINTER(c_void_p), C.POINTER(c_size_t), c_int, c_void_p, c_void_p]),

@@ -22,7 +22,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "--expt-relaxed-constexpr"]
 # bit-exact geometry / splat: never contract a*b+c into an FMA, IEEE division and sqrt (no fast math anywhere)
 PER_FILE = {
-    "dh_loss.cu": (["-DDH_LOSS_PHASE_TIMERS"] if os.environ.get("DH_LOSS_PHASE_TIMERS") else []),
+    "dh_loss.cu": (["-DDH_LOSS_PHASE_TIMERS"] if os.environ.get("DH_LOSS_PHASE_TIMERS") else []) +
+                  ([f"-DDH_LOSS_MAX_GROUPS={os.environ['DH_LOSS_MAX_GROUPS']}"] if os.environ.get("DH_LOSS_MAX_GROUPS") else []),
     "dh_geometry.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_splat.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_raster.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
                     uint32_t c = i <= w1 ? cnt[i - w0] : 0u;
                     while (__any_sync(0xFFFFFFFFu, c > 0)) {
                         const unsigned b = __ballot_sync(0xFFFFFFFFu, c > 0);
-                        const uint32_t m = c > 65535u ? 65535u : c;
+                        const uint32_t m = c > 255u ? 255u : c;
                         if (c > 0) uniq[out + __popc(b & ((1u << lane) - 1u))] = (int32_t)((uint32_t)i | (m << 16));
                         c -= m;
                         out += __popc(b);
@@ -203,35 +203,36 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
         }
     __syncthreads();
     const int box_r0 = box_sm[0], box_r1 = box_sm[1], box_s0 = box_sm[2], box_s1 = box_sm[3];
-    const int box_w = box_s1 >= box_s0 ? box_s1 - box_s0 + 1 : 0;
-    auto to_box = [&](int cell) { const int r = cell / grid; return (r - box_r0) * box_w + (cell - r * grid - box_s0); };
+    // distinct source cells -> slots (ascending cell order): is_src[cell] becomes slot + 1 (0 = not a source)
+    s = 0;
+    for (int i = c0; i < c1; ++i) s += is_src[i];
+    run = block_exclusive_scan(s, scan_smem, total);
+    const int n_usrc = total;
+    for (int i = c0; i < c1; ++i)
+        if (is_src[i]) { pv.usrc_cell[run] = (uint16_t)i; is_src[i] = ++run; }
+    __syncthreads();
     for (int sl = wid; sl < n_slices; sl += kPlanWarps) {
         const int r = sl * 32 + lane;
         const int cell = r < n_rows ? order[r] : -1;
         const int len = cell >= 0 ? ucount[cell] : 0;
         const int base = cell >= 0 ? pv.row_ptr[cell] : 0;
         pv.row_desc[r] = cell >= 0 ? ((uint32_t)cell | ((uint32_t)len << 16)) : 0u;
-        pv.row_desc_box[r] = cell >= 0 ? ((uint32_t)to_box(cell) | ((uint32_t)len << 16)) : 0u;
         uint32_t* dst = pv.ent + (size_t)soff[sl] * 32 + lane;
-        uint32_t* dst_box = pv.ent_box + (size_t)soff[sl] * 32 + lane;
         for (int k = 0; k < len; ++k) {
             const uint2 e = pv.pairs[base + k];
-            dst[(size_t)k * 32] = (e.x & 0xFFFFu) | (e.y << 12);
-            dst_box[(size_t)k * 32] = (uint32_t)to_box((int)(e.x & 0xFFFFu)) | (e.y << 12);
+            const uint32_t src = e.x & 0xFFFFu;
+            dst[(size_t)k * 32] = src | ((uint32_t)(is_src[src] - 1) << 12) | (e.y << 24);
         }
         // every row is padded to a multiple of four entries with (first source, multiplicity 0): the kernel walks whole
         // groups of four without per-entry predicates
-        for (int k = len; k < ((len + 3) & ~3); ++k) {
-            dst[(size_t)k * 32] = dst[0] & 0xFFFu;
-            dst_box[(size_t)k * 32] = dst_box[0] & 0xFFFu;
-        }
+        for (int k = len; k < ((len + 3) & ~3); ++k) dst[(size_t)k * 32] = dst[0] & 0xFFFFFFu;
     }
     if (tid == 0) {
         PlanHeader h;
         h.n_pairs = n_pairs; h.n_fg = n_fg; h.n_bg_orig = n_bg_orig; h.n_bg_trans = n_bg_trans; h.n_bg_common = n_bg_common;
         h.grid = grid; h.cap = n_fg; h.reserved = 0;
         h.box_r0 = box_r0; h.box_r1 = box_r1; h.box_s0 = box_s0; h.box_s1 = box_s1;
-        h.n_rows = n_rows; h.n_slices = n_slices; h.n_groups = n_groups; h.pad = 0;
+        h.n_rows = n_rows; h.n_slices = n_slices; h.n_groups = n_groups; h.n_usrc = n_usrc;
         *pv.hdr = h;
     }
     __syncthreads();
@@ -277,7 +278,10 @@ __global__ void __launch_bounds__(kPlanThreads) loss_plan_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int kLossThreads = 256;
 constexpr int kLossWarps = kLossThreads / 32;
-constexpr int kMaxGroups = 3;                    // groups of kLossThreads threads per CTA (one CTA per SM): 80 registers per thread
+#ifndef DH_LOSS_MAX_GROUPS
+#define DH_LOSS_MAX_GROUPS 3
+#endif
+constexpr int kMaxGroups = DH_LOSS_MAX_GROUPS;   // groups of kLossThreads threads per CTA (one CTA per SM): 3 -> 80 registers per thread
 constexpr int kPlaneCap = kMaxG * kMaxG;         // floats per tensor in the stage
 constexpr int kStageFloats = 2 * kPlaneCap;      // [cur planes][orig planes] = 32 KB
 constexpr int kOwnGroups = kPlaneCap / 4 / kLossThreads;   // float4 groups per thread at the 64x64 grid = 4
@@ -285,9 +289,9 @@ constexpr int kRowUnroll = 4;    // independent gathers in flight per thread in 
 constexpr int kWin = 16;      // up rows (columns) that can touch one native row (column): 2 * G / h <= 16 for h >= 8
 constexpr int kMaxPlanesPerItem = 2;     // resized layers: one pair of planes per item (short items balance better)
 
-struct ResizeLayout {   // float offsets into the scratch area
-    int tab, wrow, wcol, uc, uo, cnt, tmp, flat_cnt, total;
-    int box_cap;        // capacity (cells) of the box-local uc / uo / cnt arrays
+struct ResizeLayout {   // float offsets into a group's scratch area (resized planes; the flat sign counts overlay them at 0)
+    int uo, uc, gs, total;
+    int cap_usrc, cap_slots;     // capacities (float2 entries) of uo and of uc / gs
 };
 
 struct FusedLayer {
@@ -318,6 +322,8 @@ struct FusedParams {
     int scratch_floats;
     int ell_floats, ell_desc_at, ell_ent_at, ell_ent_cap;    // shared-memory copy of the sliced-ELL plan (0 = read it from global)
     int ell_slices;     // slices of the plan as the caller read them from the plan header (0 = unknown: read the header)
+    int tab_floats;     // shared-memory copy of the table blob of resized layer `tab_layer` (0 = tables are read from global)
+    int tab_layer;
     unsigned long long* debug;     // optional (DH_LOSS_DEBUG_BUF): per CTA {start ns, end ns, items, sm id}
 };
 
@@ -396,101 +402,155 @@ __device__ __forceinline__ int slice_of(int round, int wid) {
 }
 
 // ---- layers smaller than the loss grid -----------------------------------------------------------------
-// Per-layer tables, built once per (plan, layer shape) by loss_resize_setup_kernel in global memory and copied to
-// shared memory by the CTAs of loss_fused_kernel:
-//   bilinear taps of every up row / column, the up rows (columns) that touch each native row (column) with their
-//   weights (the transposed resize in gather form), up^T(background multiplicities) at native resolution, and the
-//   native box that the active up box touches.
-struct LayerTabHead {      // the part every CTA keeps in shared memory as is
-    int ty0[kMaxG], ty1[kMaxG], tx0[kMaxG], tx1[kMaxG];
-    float tly[kMaxG], tlx[kMaxG];
-    int ylo[kMaxNative], yhi[kMaxNative], xlo[kMaxNative], xhi[kMaxNative];
-    int box[8];                        // up space: r0, r1, s0, s1; native: y0, y1, x0, x1
-    int win, pad_[3];                  // longest window of up rows (columns) that touch one native row (column)
+// Per (plan, layer shape) tables, built once by loss_resize_setup_kernel into one compact blob of 32-bit words that the
+// loss kernel copies to shared memory.  A resized plane is never up-sampled as a whole: the loss needs up(orig) at the
+// distinct SOURCE cells and up(cur) at the DESTINATION rows only, and the gradient w.r.t. the native plane is a gather over
+// the destination rows that a native cell's bilinear footprint touches:
+//   src_taps[j]   the four native taps (16-bit offsets) and the two lambdas of source slot j            (uint4)
+//   dst_taps[s]   the same for the destination cell of ELL row slot s                                   (uint4)
+//   nat_ptr, nat_ent   CSR over native cells: (row slot, weight = wrow * wcol) of every destination row in the footprint
+//   wo, wt        up^T(background multiplicities) at native resolution ('global_avg' term and its gradient)
+struct TabHeader {
+    int32_t n_usrc, n_slots, n_nat, h, w, hw;
+    int32_t at_src_taps, at_dst_taps, at_nat_ptr, at_nat_ent, at_wo, at_wt, total_words;      // word offsets into the blob
+    int32_t pad[3];
 };
-struct LayerTabSmall : LayerTabHead {
-    float wrow[kMaxNative * kWin], wcol[kMaxNative * kWin];   // stride kWin here, stride `win` in shared memory
-};
-struct LayerTab : LayerTabSmall {
-    float wo[kMaxNative * kMaxNative], wt[kMaxNative * kMaxNative];
-};
-static_assert(kRowUnroll == 4, "the plan pads rows to four entries");
-static_assert(sizeof(LayerTabHead) % 16 == 0 && sizeof(LayerTabSmall) % 16 == 0 && sizeof(LayerTab) % 16 == 0, "tables are copied with 128-bit accesses");
+static_assert(sizeof(TabHeader) == 64, "the blob header is 16 words");
+
+__host__ __device__ inline size_t tab_capacity_words(int grid) {
+    const size_t cells = (size_t)grid * grid;
+    // header + taps of every cell twice + nat_ptr + 4 footprint entries per destination row + wo + wt (native <= grid)
+    return 16 + 4 * cells + 4 * cells + (cells + 4) + 2 * (4 * cells + 3 * cells) + 2 * cells + 64;
+}
 
 struct SetupParams {
     const void* plan;
     int plan_cap, G, h, w, fg_kind, bg_kind;
 };
 
-__global__ void __launch_bounds__(256) loss_resize_setup_kernel(const __grid_constant__ SetupParams p, LayerTab* __restrict__ tabs) {
+constexpr int kSetupThreads = 1024;
+
+__global__ void __launch_bounds__(kSetupThreads) loss_resize_setup_kernel(const __grid_constant__ SetupParams p, uint32_t* __restrict__ blob) {
     __shared__ float tmp[kMaxNative * kMaxG];
+    __shared__ int16_t slot_of_cell[kMaxG * kMaxG];
+    __shared__ int ty0[kMaxG], ty1[kMaxG], tx0[kMaxG], tx1[kMaxG];
+    __shared__ float tly[kMaxG], tlx[kMaxG];
+    __shared__ int ylo[kMaxNative], yhi[kMaxNative], xlo[kMaxNative], xhi[kMaxNative];
+    __shared__ float wrow[kMaxNative * kWin], wcol[kMaxNative * kWin];
+    __shared__ int scan_smem[33];
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-    LayerTab& T = tabs[0];
-    const int G = p.G, h = p.h, w = p.w;
+    const int G = p.G, h = p.h, w = p.w, hw = h * w, cells = G * G;
     const PlanView pv = plan_view(const_cast<void*>(p.plan), G, p.plan_cap);
+    const int n_usrc = p.fg_kind ? pv.hdr->n_usrc : 0;
+    const int n_slots = p.fg_kind ? pv.hdr->n_slices * 32 : 0;
     const float sy = (float)h / (float)G, sx = (float)w / (float)G;
     if (tid < G) {
-        bilinear_tap(tid, h, sy, T.ty0[tid], T.ty1[tid], T.tly[tid]);
-        bilinear_tap(tid, w, sx, T.tx0[tid], T.tx1[tid], T.tlx[tid]);
+        bilinear_tap(tid, h, sy, ty0[tid], ty1[tid], tly[tid]);
+        bilinear_tap(tid, w, sx, tx0[tid], tx1[tid], tlx[tid]);
     }
+    for (int i = tid; i < cells; i += kSetupThreads) slot_of_cell[i] = -1;
     __syncthreads();
     if (tid < h) {       // up rows that touch native row tid, and their weights
         // (taps with weight zero - the clamped rows at the top border have i1 = 1 with lambda = 0 - are not part of the window)
         int lo = G, hi = -1;
         for (int r = 0; r < G; ++r)
-            if ((T.ty0[r] == tid && T.tly[r] < 1.0f) || (T.ty1[r] == tid && T.tly[r] > 0.0f)) { lo = min(lo, r); hi = max(hi, r); }
+            if ((ty0[r] == tid && tly[r] < 1.0f) || (ty1[r] == tid && tly[r] > 0.0f)) { lo = min(lo, r); hi = max(hi, r); }
         hi = min(hi, lo + kWin - 1);
-        T.ylo[tid] = lo; T.yhi[tid] = hi;
+        ylo[tid] = lo; yhi[tid] = hi;
         for (int r = lo; r <= hi; ++r)
-            T.wrow[tid * kWin + r - lo] = (T.ty0[r] == tid ? 1.0f - T.tly[r] : 0.0f) + (T.ty1[r] == tid ? T.tly[r] : 0.0f);
+            wrow[tid * kWin + r - lo] = (ty0[r] == tid ? 1.0f - tly[r] : 0.0f) + (ty1[r] == tid ? tly[r] : 0.0f);
     }
     if (tid >= 64 && tid - 64 < w) {
         const int j = tid - 64;
         int lo = G, hi = -1;
         for (int s = 0; s < G; ++s)
-            if ((T.tx0[s] == j && T.tlx[s] < 1.0f) || (T.tx1[s] == j && T.tlx[s] > 0.0f)) { lo = min(lo, s); hi = max(hi, s); }
+            if ((tx0[s] == j && tlx[s] < 1.0f) || (tx1[s] == j && tlx[s] > 0.0f)) { lo = min(lo, s); hi = max(hi, s); }
         hi = min(hi, lo + kWin - 1);
-        T.xlo[j] = lo; T.xhi[j] = hi;
+        xlo[j] = lo; xhi[j] = hi;
         for (int s = lo; s <= hi; ++s)
-            T.wcol[j * kWin + s - lo] = (T.tx0[s] == j ? 1.0f - T.tlx[s] : 0.0f) + (T.tx1[s] == j ? T.tlx[s] : 0.0f);
+            wcol[j * kWin + s - lo] = (tx0[s] == j ? 1.0f - tlx[s] : 0.0f) + (tx1[s] == j ? tlx[s] : 0.0f);
     }
-    if (tid == 128) {
-        const bool full = p.bg_kind == 2;      // local_avg needs up() on every background cell
-        const bool none = !p.fg_kind && !full;
-        const int r0 = full ? 0 : (none ? G : pv.hdr->box_r0), r1 = full ? G - 1 : (none ? -1 : pv.hdr->box_r1);
-        const int s0 = full ? 0 : (none ? G : pv.hdr->box_s0), s1 = full ? G - 1 : (none ? -1 : pv.hdr->box_s1);
-        const bool any = r1 >= r0;
-        T.box[0] = r0; T.box[1] = r1; T.box[2] = s0; T.box[3] = s1;
-        T.box[4] = any ? T.ty0[r0] : 0; T.box[5] = any ? T.ty1[r1] : -1;
-        T.box[6] = any ? T.tx0[s0] : 0; T.box[7] = any ? T.tx1[s1] : -1;
+    for (int sl = tid; sl < n_slots; sl += kSetupThreads) {
+        const uint32_t d = pv.row_desc[sl];
+        if (d >> 16) slot_of_cell[d & 0xFFFFu] = (int16_t)sl;
     }
     __syncthreads();
-    if (tid == 0) {
-        int win = 1;
-        for (int i = 0; i < h; ++i) win = max(win, T.yhi[i] - T.ylo[i] + 1);
-        for (int j = 0; j < w; ++j) win = max(win, T.xhi[j] - T.xlo[j] + 1);
-        T.win = win;
+    // blob layout (compact)
+    TabHeader H;
+    H.n_usrc = n_usrc; H.n_slots = n_slots; H.h = h; H.w = w; H.hw = hw;
+    H.at_src_taps = 16;
+    H.at_dst_taps = H.at_src_taps + 4 * n_usrc;
+    H.at_nat_ptr = H.at_dst_taps + 4 * n_slots;
+    H.at_nat_ent = H.at_nat_ptr + (hw + 1 + 3) / 4 * 4;
+    // native CSR: count, scan, fill - every native cell walks the up cells of its footprint in raster order (deterministic)
+    int cnt = 0;
+    int my_first = 0;
+    // every thread owns a contiguous run of native cells
+    const int per = (hw + kSetupThreads - 1) / kSetupThreads;
+    const int n0 = min(hw, tid * per), n1 = min(hw, n0 + per);
+    for (int n = n0; n < n1; ++n) {
+        const int y = n / w, x = n - y * w;
+        for (int r = ylo[y]; r <= yhi[y]; ++r)
+            for (int s2 = xlo[x]; s2 <= xhi[x]; ++s2) cnt += slot_of_cell[r * G + s2] >= 0 ? 1 : 0;
+        cnt = (cnt + 3) & ~3;       // every native cell's list is padded to a multiple of four (weight 0): unrolled gather
+    }
+    int total;
+    my_first = block_exclusive_scan(cnt, scan_smem, total);
+    H.n_nat = total;
+    H.at_wo = H.at_nat_ent + (2 * total + 3) / 4 * 4;
+    H.at_wt = H.at_wo + (hw + 3) / 4 * 4;
+    H.total_words = H.at_wt + (hw + 3) / 4 * 4;
+    H.pad[0] = H.pad[1] = H.pad[2] = 0;
+    if (tid == 0) *reinterpret_cast<TabHeader*>(blob) = H;
+    {
+        int32_t* nat_ptr = reinterpret_cast<int32_t*>(blob + H.at_nat_ptr);
+        uint2* nat_ent = reinterpret_cast<uint2*>(blob + H.at_nat_ent);
+        int o = my_first;
+        for (int n = n0; n < n1; ++n) {
+            nat_ptr[n] = o;
+            const int y = n / w, x = n - y * w;
+            for (int r = ylo[y]; r <= yhi[y]; ++r)
+                for (int s2 = xlo[x]; s2 <= xhi[x]; ++s2) {
+                    const int sl = slot_of_cell[r * G + s2];
+                    if (sl >= 0) nat_ent[o++] = make_uint2((uint32_t)sl, __float_as_uint(wrow[y * kWin + r - ylo[y]] * wcol[x * kWin + s2 - xlo[x]]));
+                }
+            while ((o - nat_ptr[n]) & 3) nat_ent[o++] = make_uint2(0u, 0u);      // padding: slot 0 with weight 0
+        }
+        if (tid == 0) nat_ptr[hw] = total;
+    }
+    // taps of the source slots and of the destination rows
+    auto taps_of = [&](int cell) {
+        const int r = cell / G, s2 = cell - r * G;
+        const uint32_t y0 = (uint32_t)(ty0[r] * w), y1 = (uint32_t)(ty1[r] * w), x0 = (uint32_t)tx0[s2], x1 = (uint32_t)tx1[s2];
+        return make_uint4((y0 + x0) | ((y0 + x1) << 16), (y1 + x0) | ((y1 + x1) << 16), __float_as_uint(tlx[s2]), __float_as_uint(tly[r]));
+    };
+    uint4* src_taps = reinterpret_cast<uint4*>(blob + H.at_src_taps);
+    uint4* dst_taps = reinterpret_cast<uint4*>(blob + H.at_dst_taps);
+    for (int j = tid; j < n_usrc; j += kSetupThreads) src_taps[j] = taps_of((int)pv.usrc_cell[j]);
+    for (int sl = tid; sl < n_slots; sl += kSetupThreads) {
+        const uint32_t d = pv.row_desc[sl];
+        dst_taps[sl] = (d >> 16) ? taps_of((int)(d & 0xFFFFu)) : make_uint4(0u, 0u, 0u, 0u);
     }
     // wo / wt = up^T applied to the background multiplicities (separable, via tmp)
     for (int pass = 0; pass < 2; ++pass) {
-        float* dst = pass == 0 ? T.wo : T.wt;
-        for (int yi = wid; yi < h; yi += 8)
-            for (int s = lane; s < G; s += 32) {
+        float* dst = reinterpret_cast<float*>(blob + (pass == 0 ? H.at_wo : H.at_wt));
+        __syncthreads();
+        for (int y = wid; y < h; y += kSetupThreads / 32)
+            for (int s2 = lane; s2 < G; s2 += 32) {
                 float a = 0.0f;
-                for (int r = T.ylo[yi]; r <= T.yhi[yi]; ++r) {
-                    const ushort4 bc = pv.bgcnt[r * G + s];
-                    a = fmaf(T.wrow[yi * kWin + r - T.ylo[yi]], (float)(pass == 0 ? bc.x : bc.y), a);
+                for (int r = ylo[y]; r <= yhi[y]; ++r) {
+                    const ushort4 bc = pv.bgcnt[r * G + s2];
+                    a = fmaf(wrow[y * kWin + r - ylo[y]], (float)(pass == 0 ? bc.x : bc.y), a);
                 }
-                tmp[yi * G + s] = a;
+                tmp[y * G + s2] = a;
             }
         __syncthreads();
-        for (int yi = wid; yi < h; yi += 8)
-            for (int xj = lane; xj < w; xj += 32) {
+        for (int y = wid; y < h; y += kSetupThreads / 32)
+            for (int x = lane; x < w; x += 32) {
                 float a = 0.0f;
-                for (int s = T.xlo[xj]; s <= T.xhi[xj]; ++s) a = fmaf(T.wcol[xj * kWin + s - T.xlo[xj]], tmp[yi * G + s], a);
-                dst[yi * w + xj] = a;
+                for (int s2 = xlo[x]; s2 <= xhi[x]; ++s2) a = fmaf(wcol[x * kWin + s2 - xlo[x]], tmp[y * G + s2], a);
+                dst[y * w + x] = a;
             }
-        __syncthreads();
     }
 }
 
@@ -542,7 +602,9 @@ __device__ __forceinline__ void pair_term(float fm, float d, float& acc, float& 
 // memory (the pair entries are re-read for every plane; from L1 / L2 they were the dominant stall).
 // kG = 64: the loss grid of the reference; kG = 0: any grid <= 64.
 // kBinary: every background multiplicity is 0 or 1 (lists from np.nonzero) -> register bit masks for the own cells.
-template <int kG, bool kBinary>
+// kMem: 0 = the ELL plan and the resize tables are read from global memory (through L1), 1 = the plan is in shared memory,
+// 2 = the plan and the tables of the (single) resized layer are.  A template parameter so that the accesses compile to LDS.
+template <int kG, bool kBinary, int kMem>
 __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) float fsm[];
     __shared__ __align__(16) FusedShared shg[kMaxGroups];
@@ -551,7 +613,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
 #ifdef DH_LOSS_PHASE_TIMERS
     const long long dbg_clock0 = clock64();
 #endif
-    float* const gbase = fsm + p.ell_floats + (size_t)gid * (kStageFloats + p.scratch_floats);
+    float* const gbase = fsm + p.ell_floats + p.tab_floats + (size_t)gid * (kStageFloats + p.scratch_floats);
     float* const st_cur = gbase;                      // the stage: [cur planes][orig planes]
     float* const st_org = gbase + kPlaneCap;
     float* const scratch = gbase + kStageFloats;
@@ -585,23 +647,22 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
     const PlanView& pv = p.pv;
     const int n_slices = p.fg_kind ? (p.ell_slices ? p.ell_slices : pv.hdr->n_slices) : 0;
     const int n_rounds = (n_slices + kLossWarps - 1) / kLossWarps;
-    // the sliced-ELL plan: one copy in shared memory for all groups when it fits (ell_floats != 0), else read through L1
-    const int32_t* ell_off = pv.ell_off;
-    const uint32_t* row_desc = pv.row_desc;
-    const uint32_t* ent = pv.ent;
-    if (p.ell_floats) {
+    // the sliced-ELL plan: one copy in shared memory for all groups (kMem >= 1), else read through L1
+    const uint32_t* const s_words = reinterpret_cast<const uint32_t*>(fsm);
+    if (kMem) {
         const int n_groups32 = p.fg_kind ? p.ell_ent_cap : 0;       // (the caller's ell_groups * 32)
         int32_t* s_off = reinterpret_cast<int32_t*>(fsm);
         uint32_t* s_desc = reinterpret_cast<uint32_t*>(fsm) + p.ell_desc_at;
         uint32_t* s_ent = reinterpret_cast<uint32_t*>(fsm) + p.ell_ent_at;
-        {
-            for (int i = threadIdx.x; i <= n_slices; i += blockDim.x) s_off[i] = pv.ell_off[i];
-            for (int i = threadIdx.x; i < n_slices * 32; i += blockDim.x) s_desc[i] = pv.row_desc[i];
-            for (int i = threadIdx.x; i < n_groups32 / 4; i += blockDim.x)
-                reinterpret_cast<uint4*>(s_ent)[i] = reinterpret_cast<const uint4*>(pv.ent)[i];
-            ell_off = s_off; row_desc = s_desc; ent = s_ent;
-        }
+        for (int i = threadIdx.x; i <= n_slices; i += blockDim.x) s_off[i] = pv.ell_off[i];
+        for (int i = threadIdx.x; i < n_slices * 32; i += blockDim.x) s_desc[i] = pv.row_desc[i];
+        for (int i = threadIdx.x; i < n_groups32 / 4; i += blockDim.x)
+            reinterpret_cast<uint4*>(s_ent)[i] = reinterpret_cast<const uint4*>(pv.ent)[i];
     }
+    auto ell_off_of = [&](int sl) -> int { return kMem ? (int)s_words[sl] : __ldg(pv.ell_off + sl); };
+    auto row_desc_of = [&](int i) -> uint32_t { return kMem ? s_words[p.ell_desc_at + i] : __ldg(pv.row_desc + i); };
+    auto entries_of = [&](int sl) -> const uint32_t* { return (kMem ? s_words + p.ell_ent_at : pv.ent) + ell_off_of(sl) * 32; };
+    auto ld_ent = [&](const uint32_t* q) -> uint32_t { return kMem ? *q : __ldg(q); };
     // membership of the own cells (flat layers) in the three background lists and in the set of destination rows, as
     // 16-bit masks (bit 4k+i = cell i of group k), precomputed by the plan.  Lists that come from np.nonzero never repeat a
     // cell; if a generic caller does, the multiplicities are re-read from the plan in the (slower) general path.
@@ -623,35 +684,26 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
     }
     const float inv_no = 1.0f / (float)p.n_bg_orig, inv_nt = 1.0f / (float)p.n_bg_trans;
 
-    // resized layers: scratch views and the active box (identical in every layer's table).  Two planes are processed at a
-    // time (float2 per cell), so that the index arithmetic of the resize and of the pair walk is paid once per pair of planes.
+    // resized layers: two planes are processed at a time (float2 per slot), so that the index arithmetic of the resize and of
+    // the pair walk is paid once per pair of planes
     const ResizeLayout& lay = p.lay;
-    LayerTabHead& T = *reinterpret_cast<LayerTabHead*>(scratch + lay.tab);
-    float* const swrow = scratch + lay.wrow;       // [h][win], [w][win]
-    float* const swcol = scratch + lay.wcol;
-    float2* const suc = reinterpret_cast<float2*>(scratch + lay.uc);     // box-local: index (r - br0) * bw + (s - bs0)
-    float2* const suo = reinterpret_cast<float2*>(scratch + lay.uo);
-    float2* const gu = reinterpret_cast<float2*>(scratch + lay.cnt);     // sign counts, then the gradient w.r.t. up(cur)
-    float2* const tmp = reinterpret_cast<float2*>(scratch + lay.tmp);    // (overlays uc / uo, which are dead by then)
-    float* const cntb = scratch + lay.flat_cnt;                          // sign counts of a flat plane
-    int br0 = 0, br1 = -1, bs0 = 0, bs1 = -1;
-    if (p.n_small_items) {
-        const LayerTab* tab0 = nullptr;
-#pragma unroll
-        for (int i = kMaxLossLayers - 1; i >= 0; --i)
-            if (i < p.n_layers && !p.lv[i].flat) tab0 = static_cast<const LayerTab*>(p.lv[i].tab);
-        br0 = tab0->box[0]; br1 = tab0->box[1]; bs0 = tab0->box[2]; bs1 = tab0->box[3];
+    float2* const uo2 = reinterpret_cast<float2*>(scratch + lay.uo);     // up(orig) at the distinct source cells (slot order)
+    float2* const uc2 = reinterpret_cast<float2*>(scratch + lay.uc);     // up(cur) at the destination rows (ELL row slot order)
+    float2* const gs2 = reinterpret_cast<float2*>(scratch + lay.gs);     // sign counts of the destination rows
+    float* const cntb = scratch;                                         // sign counts of a flat plane (overlays the above)
+    // the table blob of one resized layer lives in shared memory behind the ELL plan, shared by the groups
+    const uint32_t* const s_tab = reinterpret_cast<const uint32_t*>(fsm) + p.ell_floats;
+    if (kMem == 2) {
+        const uint32_t* g_tab = static_cast<const uint32_t*>(p.lv[p.tab_layer].tab);
+        const int words = min(p.tab_floats, (int)reinterpret_cast<const TabHeader*>(g_tab)->at_wo);      // (wo / wt stay in global memory)
+        for (int i = threadIdx.x; i < words / 4; i += blockDim.x)
+            reinterpret_cast<uint4*>(fsm + p.ell_floats)[i] = reinterpret_cast<const uint4*>(g_tab)[i];
     }
-    const bool any_box = br1 >= br0;
-    const int bw = any_box ? bs1 - bs0 + 1 : 0, bh = any_box ? br1 - br0 + 1 : 0;
-    const int bcells = bw * bh;
-    const bool box_overflow = bcells > lay.box_cap;   // the caller under-sized the box-local buffers: poison, never corrupt
-    const int boff = br0 * bw + bs0;
-    const unsigned bw_magic = bw > 1 ? (unsigned)((0x100000000ull + bw - 1) / bw) : 0xFFFFFFFFu;     // floor(i / bw) = umulhi(i, magic), i < 2^20
-    auto to_box = [&](int cell) { const int r = kG ? cell >> 6 : cell / G; return r * bw + (cell - r * G) - boff; };
     __syncthreads();
 
-    int cur_layer = -1;          // resized layer whose tables are in shared memory
+    int prev_kind = -1;          // 0 = flat, 1 = resized: kind of this group's previous item (they share the scratch area)
+    int wt_layer = -1;
+    float wt_reg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     uint32_t phase = 0;
     unsigned long long dbg_t0 = 0, dbg_items = 0;
     if (p.debug && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
@@ -713,24 +765,25 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
             }
             // the scratch area may still be read by slow warps (sign counts of the previous plane, a resized plane's buffers)
             group_sync(gid);
+            prev_kind = 0;
             // Destination rows: one thread per destination cell, its sources from the sliced-ELL plan
             for (int rd = 0; rd < n_rounds; ++rd) {
                 const int sl = slice_of(rd, wid);
                 if (sl >= n_slices) break;
-                const uint32_t desc = row_desc[sl * 32 + lane];
+                const uint32_t desc = row_desc_of(sl * 32 + lane);
                 const int len = (int)(desc >> 16), dcell = (int)(desc & 0xFFFFu);
-                const uint32_t* e_ptr = ent + ell_off[sl] * 32 + lane;
+                const uint32_t* e_ptr = entries_of(sl) + lane;
                 const float cval = st_cur[dcell];
                 float cn = 0.0f;
                 for (int k = 0; k < len; k += kRowUnroll) {
                     uint32_t e[kRowUnroll];
                     float o[kRowUnroll];
 #pragma unroll
-                    for (int u = 0; u < kRowUnroll; ++u) e[u] = e_ptr[(k + u) * 32];      // (rows are padded to a multiple of kRowUnroll)
+                    for (int u = 0; u < kRowUnroll; ++u) e[u] = ld_ent(e_ptr + (k + u) * 32);      // (rows are padded to a multiple of kRowUnroll)
 #pragma unroll
                     for (int u = 0; u < kRowUnroll; ++u) o[u] = st_org[e[u] & 0xFFFu];
 #pragma unroll
-                    for (int u = 0; u < kRowUnroll; ++u) pair_term((float)(e[u] >> 12), o[u] - cval, sums[0], cn);   // (m = 0: no-op)
+                    for (int u = 0; u < kRowUnroll; ++u) pair_term((float)(e[u] >> 24), o[u] - cval, sums[0], cn);   // (m = 0 in the padding: no-op)
                 }
                 if (len) cntb[dcell] = cn;
             }
@@ -776,84 +829,55 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
         } else {
             // ------------------------------------------------------------------ planes of a layer below the loss grid
             const int h = L.h, w = L.w, hw = h * w;
-            const LayerTab* const tl = static_cast<const LayerTab*>(L.tab);
-            const float* __restrict__ gwo = tl->wo;      // up^T(background multiplicities), read through L1
-            const float* __restrict__ gwt = tl->wt;
-            if (l != cur_layer) {       // (a CTA crosses a layer boundary a handful of times)
-                group_sync(gid);        // slow warps may still read the previous layer's tables
-                const float4* src = reinterpret_cast<const float4*>(static_cast<const LayerTabHead*>(tl));
-                float4* dst = reinterpret_cast<float4*>(&T);
-                for (int i = tid; i < (int)(sizeof(LayerTabHead) / 16); i += kLossThreads) dst[i] = src[i];
-                const int win = tl->win;
-                for (int i = tid; i < h * win; i += kLossThreads) swrow[i] = tl->wrow[(i / win) * kWin + i % win];
-                for (int i = tid; i < w * win; i += kLossThreads) swcol[i] = tl->wcol[(i / win) * kWin + i % win];
-                cur_layer = l;
+            const uint32_t* const tab = kMem == 2 ? s_tab : static_cast<const uint32_t*>(L.tab);      // (kMem 2: one resized layer)
+            const TabHeader& TH = *reinterpret_cast<const TabHeader*>(tab);
+            const int n_usrc = TH.n_usrc, n_slots = TH.n_slots;
+            const uint4* const src_taps = reinterpret_cast<const uint4*>(tab + TH.at_src_taps);
+            const uint4* const dst_taps = reinterpret_cast<const uint4*>(tab + TH.at_dst_taps);
+            const int32_t* const nat_ptr = reinterpret_cast<const int32_t*>(tab + TH.at_nat_ptr);
+            const uint2* const nat_ent = reinterpret_cast<const uint2*>(tab + TH.at_nat_ent);
+            const float* __restrict__ two = reinterpret_cast<const float*>(static_cast<const uint32_t*>(L.tab) + TH.at_wo);   // up^T(background
+            const float* __restrict__ twt = reinterpret_cast<const float*>(static_cast<const uint32_t*>(L.tab) + TH.at_wt);   // multiplicities): L1
+            const bool overflow = n_usrc > lay.cap_usrc || n_slots > lay.cap_slots;      // under-sized buffers: poison, never corrupt
+            if (prev_kind == 0) group_sync(gid);      // slow warps may still read the sign counts of a flat plane
+            prev_kind = 1;
+            if (wt_layer != l) {        // this thread's cells of up^T(bg_trans multiplicities): the same for every plane of the layer
+                wt_layer = l;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wt_reg[i] = (p.bg_kind == 1 && tid + i * kLossThreads < hw) ? __ldg(twt + tid + i * kLossThreads) : 0.0f;
             }
             for (int pl = 0; pl < planes; pl += 2) {
                 const int c = c0 + pl;
-                const bool two = pl + 1 < planes;          // an odd plane at the end is paired with itself, its copy is not stored
+                const bool two_planes = pl + 1 < planes;   // an odd plane at the end is paired with itself, its copy is not stored
                 const float* const pc0 = st_cur + pl * hw;
                 const float* const po0 = st_org + pl * hw;
-                const float* const pc1 = two ? pc0 + hw : pc0;
-                const float* const po1 = two ? po0 + hw : po0;
+                const float* const pc1 = two_planes ? pc0 + hw : pc0;
+                const float* const po1 = two_planes ? po0 + hw : po0;
                 const bool last_pair = pl + 2 >= planes;
-                group_sync(gid);          // tables loaded; scratch of the previous pair / flat item no longer read
-                if (box_overflow) {
+                if (overflow) {
                     if (tid == 0) {
-                        for (int j = 0; j < (two ? 2 : 1); ++j) {
+                        for (int j = 0; j < (two_planes ? 2 : 1); ++j) {
                             p.partial[2 * (L.partial_begin + c + j)] = __int_as_float(0x7FC00000);
                             p.partial[2 * (L.partial_begin + c + j) + 1] = __int_as_float(0x7FC00000);
                         }
-                        if (last_pair) stage_item(next_item);
                     }
+                    group_sync(gid);
+                    if (last_pair && tid == 0) stage_item(next_item);
                     continue;
                 }
-                const int win = T.win;
-                const int ny0 = T.box[4], ny1 = T.box[5], nx0 = T.box[6], nx1 = T.box[7];
-                // up(cur), up(orig) inside the box (and the box-local sign counts start at zero)
-                for (int i = tid; i < bcells; i += kLossThreads) gu[i] = make_float2(0.0f, 0.0f);
-                for (int b = tid; b < bcells; b += kLossThreads) {        // (flat over the box: every lane busy)
-                    const int rr = (int)__umulhi((unsigned)b, bw_magic), r = br0 + rr, s = bs0 + b - rr * bw;
-                    const int y0 = T.ty0[r] * w, y1 = T.ty1[r] * w;
-                    const float ly = T.tly[r], hy = 1.0f - ly;
-                    const int x0 = T.tx0[s], x1 = T.tx1[s];
-                    const float lx = T.tlx[s], hx = 1.0f - lx;
-                    const int i00 = y0 + x0, i01 = y0 + x1, i10 = y1 + x0, i11 = y1 + x1;
-                    suc[b] = make_float2(hy * (hx * pc0[i00] + lx * pc0[i01]) + ly * (hx * pc0[i10] + lx * pc0[i11]),
-                                         hy * (hx * pc1[i00] + lx * pc1[i01]) + ly * (hx * pc1[i10] + lx * pc1[i11]));
-                    suo[b] = make_float2(hy * (hx * po0[i00] + lx * po0[i01]) + ly * (hx * po0[i10] + lx * po0[i11]),
-                                         hy * (hx * po1[i00] + lx * po1[i01]) + ly * (hx * po1[i10] + lx * po1[i11]));
-                }
-                group_sync(gid);
-                DH_PH(2)
+                // up(orig) at the source slots, up(cur) at the destination rows: four taps each
+                auto bilerp2 = [&](const uint4 t, const float* q0, const float* q1) {
+                    const int i00 = (int)(t.x & 0xFFFFu), i01 = (int)(t.x >> 16), i10 = (int)(t.y & 0xFFFFu), i11 = (int)(t.y >> 16);
+                    const float lx = __uint_as_float(t.z), ly = __uint_as_float(t.w), hx = 1.0f - lx, hy = 1.0f - ly;
+                    return make_float2(hy * (hx * q0[i00] + lx * q0[i01]) + ly * (hx * q0[i10] + lx * q0[i11]),
+                                       hy * (hx * q1[i00] + lx * q1[i01]) + ly * (hx * q1[i10] + lx * q1[i11]));
+                };
+                for (int j = tid; j < n_usrc; j += kLossThreads) uo2[j] = bilerp2(src_taps[j], po0, po1);
+                for (int j = tid; j < n_slots; j += kLossThreads) uc2[j] = bilerp2(dst_taps[j], pc0, pc1);
                 float sums[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // per plane: foreground sum, two background sums
-                for (int rd = 0; rd < n_rounds; ++rd) {
-                    const int sl = slice_of(rd, wid);
-                    if (sl >= n_slices) break;
-                    const uint32_t desc = row_desc[sl * 32 + lane];
-                    const int len = (int)(desc >> 16), db = len ? to_box((int)(desc & 0xFFFFu)) : 0;
-                    const uint32_t* e_ptr = ent + ell_off[sl] * 32 + lane;
-                    const float2 cval = suc[db];
-                    float cn0 = 0.0f, cn1 = 0.0f;
-                    for (int k = 0; k < len; k += kRowUnroll) {
-                        uint32_t e[kRowUnroll];
-                        float2 o[kRowUnroll];
-#pragma unroll
-                        for (int u = 0; u < kRowUnroll; ++u) e[u] = e_ptr[(k + u) * 32];      // (rows are padded to a multiple of kRowUnroll)
-#pragma unroll
-                        for (int u = 0; u < kRowUnroll; ++u) o[u] = suo[to_box((int)(e[u] & 0xFFFu))];
-#pragma unroll
-                        for (int u = 0; u < kRowUnroll; ++u) {
-                            const float fm = (float)(e[u] >> 12);          // (m = 0 past the end of the row: no-op)
-                            pair_term(fm, o[u].x - cval.x, sums[0], cn0);
-                            pair_term(fm, o[u].y - cval.y, sums[3], cn1);
-                        }
-                    }
-                    if (len) gu[db] = make_float2(cn0, cn1);
-                }
                 if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
                     for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(gwo + i)), e = __ldg(reinterpret_cast<const float4*>(gwt + i));
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(two + i)), e = __ldg(reinterpret_cast<const float4*>(twt + i));
                         const float4 b0 = *reinterpret_cast<const float4*>(po0 + i), f0 = *reinterpret_cast<const float4*>(pc0 + i);
                         const float4 b1 = *reinterpret_cast<const float4*>(po1 + i), f1 = *reinterpret_cast<const float4*>(pc1 + i);
                         sums[1] = fmaf(a.x, b0.x, fmaf(a.y, b0.y, fmaf(a.z, b0.z, fmaf(a.w, b0.w, sums[1]))));
@@ -861,13 +885,32 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                         sums[4] = fmaf(a.x, b1.x, fmaf(a.y, b1.y, fmaf(a.z, b1.z, fmaf(a.w, b1.w, sums[4]))));
                         sums[5] = fmaf(e.x, f1.x, fmaf(e.y, f1.y, fmaf(e.z, f1.z, fmaf(e.w, f1.w, sums[5]))));
                     }
-                } else if (p.bg_kind == 2) {       // box = whole grid
-                    for (int q = tid; q < GG; q += kLossThreads) {
-                        const float mz = (float)pv.bgcnt[q].z;
-                        const float2 uo = suo[q], uc = suc[q];
-                        sums[1] = fmaf(mz, fabsf(uo.x - uc.x), sums[1]);
-                        sums[4] = fmaf(mz, fabsf(uo.y - uc.y), sums[4]);
+                }
+                group_sync(gid);          // (also: every warp is past the gradient gather of the previous pair, gs2 can be rewritten)
+                DH_PH(2)
+                for (int rd = 0; rd < n_rounds; ++rd) {
+                    const int sl = slice_of(rd, wid);
+                    if (sl >= n_slices) break;
+                    const int slot = sl * 32 + lane;
+                    const int len = (int)(row_desc_of(slot) >> 16);
+                    const uint32_t* e_ptr = entries_of(sl) + lane;
+                    const float2 cval = uc2[slot];
+                    float cn0 = 0.0f, cn1 = 0.0f;
+                    for (int k = 0; k < len; k += kRowUnroll) {
+                        uint32_t e[kRowUnroll];
+                        float2 o[kRowUnroll];
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) e[u] = ld_ent(e_ptr + (k + u) * 32);      // (rows are padded to a multiple of kRowUnroll)
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) o[u] = uo2[(e[u] >> 12) & 0xFFFu];
+#pragma unroll
+                        for (int u = 0; u < kRowUnroll; ++u) {
+                            const float fm = (float)(e[u] >> 24);          // (m = 0 in the padding: no-op)
+                            pair_term(fm, o[u].x - cval.x, sums[0], cn0);
+                            pair_term(fm, o[u].y - cval.y, sums[3], cn1);
+                        }
                     }
+                    gs2[slot] = make_float2(cn0, cn1);
                 }
                 DH_PH(3)
                 block_sum<6>(sums, sh.red, gid);
@@ -880,66 +923,43 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                         const float d0 = sums[1] * inv_no - sums[2] * inv_nt, d1 = sums[4] * inv_no - sums[5] * inv_nt;
                         bg0 = fabsf(d0); bg1 = fabsf(d1);
                         bscale0 = -sgn(d0) * gscale; bscale1 = -sgn(d1) * gscale;
-                    } else if (p.bg_kind == 2) {
-                        bg0 = sums[1]; bg1 = sums[4];
                     }
                     if (tid == 0) {
                         p.partial[2 * (L.partial_begin + c)] = sums[0]; p.partial[2 * (L.partial_begin + c) + 1] = bg0;
-                        if (two) { p.partial[2 * (L.partial_begin + c + 1)] = sums[3]; p.partial[2 * (L.partial_begin + c + 1) + 1] = bg1; }
+                        if (two_planes) { p.partial[2 * (L.partial_begin + c + 1)] = sums[3]; p.partial[2 * (L.partial_begin + c + 1) + 1] = bg1; }
                     }
                 }
+                DH_PH(5)
                 if (L.grad) {
+                    // gradient at native resolution: every native cell gathers the sign counts of the destination rows in its
+                    // bilinear footprint (weights = transposed resize), plus the background term
                     float* g0 = L.grad + (size_t)c * hw;
-                    // gradient w.r.t. up(cur) inside the box (in place: sign count -> gradient), then up^T in gather form
-                    for (int i = tid; i < bcells; i += kLossThreads) {
-                        float2 v = gu[i];
-                        v.x *= fscale; v.y *= fscale;
-                        if (p.bg_kind == 2) {
-                            const float mz = (float)pv.bgcnt[i].z * lscale;
-                            const float2 uo = suo[i], uc = suc[i];
-                            v.x -= sgn(uo.x - uc.x) * mz; v.y -= sgn(uo.y - uc.y) * mz;
-                        }
-                        gu[i] = v;
-                    }
-                    group_sync(gid);
-                    for (int i = tid; i < (ny1 - ny0 + 1) * bw; i += kLossThreads) {       // (flat over native rows x box columns)
-                        const int yr = (int)__umulhi((unsigned)i, bw_magic), yi = ny0 + yr, sc = i - yr * bw;
-                        const int lo = T.ylo[yi];
-                        const int ra = max(lo, br0), rb = min(T.yhi[yi], br1);
-                        const float* wr = swrow + yi * win - lo;
+                    auto gather_cell = [&](int n, float wtv) {
                         float a0 = 0.0f, a1 = 0.0f;
-                        const float2* gp = gu + sc - br0 * bw;
-                        for (int r = ra; r <= rb; ++r) {
-                            const float2 gv = gp[r * bw];
-                            a0 = fmaf(wr[r], gv.x, a0); a1 = fmaf(wr[r], gv.y, a1);
-                        }
-                        tmp[yi * G + bs0 + sc] = make_float2(a0, a1);
-                    }
-                    group_sync(gid);
-                    DH_PH(5)
-                    for (int yi = wid; yi < h; yi += kLossWarps) {
-                        const bool row_in = yi >= ny0 && yi <= ny1;
-                        for (int xj = lane; xj < w; xj += 32) {
-                            float a0 = 0.0f, a1 = 0.0f;
-                            if (row_in && xj >= nx0 && xj <= nx1) {
-                                const int lo = T.xlo[xj];
-                                const int sa = max(lo, bs0), sb = min(T.xhi[xj], bs1);
-                                const float* wc = swcol + xj * win - lo;
-                                const float2* tp = tmp + yi * G;
-                                for (int s = sa; s <= sb; ++s) {
-                                    const float2 tv = tp[s];
-                                    a0 = fmaf(wc[s], tv.x, a0); a1 = fmaf(wc[s], tv.y, a1);
-                                }
+                        const int k1 = nat_ptr[n + 1];
+                        for (int k = nat_ptr[n]; k < k1; k += 4) {       // (lists are padded to a multiple of four)
+                            uint2 ne[4];
+                            float2 gv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) ne[u] = nat_ent[k + u];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) gv[u] = gs2[ne[u].x];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float wv = __uint_as_float(ne[u].y);
+                                a0 = fmaf(wv, gv[u].x, a0); a1 = fmaf(wv, gv[u].y, a1);
                             }
-                            if (p.bg_kind == 1) {
-                                const float wtv = __ldg(gwt + yi * w + xj);
-                                a0 = fmaf(bscale0, wtv, a0); a1 = fmaf(bscale1, wtv, a1);
-                            }
-                            g0[yi * w + xj] = a0;
-                            if (two) g0[hw + yi * w + xj] = a1;
                         }
-                    }
+                        a0 = fmaf(bscale0, wtv, a0 * fscale); a1 = fmaf(bscale1, wtv, a1 * fscale);
+                        g0[n] = a0;
+                        if (two_planes) g0[hw + n] = a1;
+                    };
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (tid + i * kLossThreads < hw) gather_cell(tid + i * kLossThreads, wt_reg[i]);
+                    for (int n = tid + 4 * kLossThreads; n < hw; n += kLossThreads) gather_cell(n, p.bg_kind == 1 ? __ldg(twt + n) : 0.0f);
                 }
+                DH_PH(7)
             }
             DH_PH(7)
         }
@@ -1046,34 +1066,38 @@ size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels) {
     return loss_ws_layout((size_t)n_layers * max_channels, &a);
 }
 
-size_t dh_loss_resize_tables_bytes(void) { return sizeof(LayerTab); }
+size_t dh_loss_resize_tables_bytes(void) { return sizeof(uint32_t) * tab_capacity_words(kMaxG); }
 
 int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int w, int fg_kind, int bg_kind, void* tables,
                                 void* stream) {
     DH_REQUIRE(plan && tables && grid >= 1 && grid <= kMaxG && h >= 1 && w >= 1 && n_fg >= 0);
     if (h > grid || w > grid || h > kMaxNative || w > kMaxNative) return DH_ERR_UNSUPPORTED;
     if (2 * ((grid + h - 1) / h) > kWin || 2 * ((grid + w - 1) / w) > kWin) return DH_ERR_UNSUPPORTED;
+    if (h * w > 65535) return DH_ERR_UNSUPPORTED;      // 16-bit tap offsets
     SetupParams sp;
     sp.plan = plan; sp.plan_cap = n_fg; sp.G = grid; sp.h = h; sp.w = w; sp.fg_kind = fg_kind; sp.bg_kind = bg_kind;
-    loss_resize_setup_kernel<<<1, 256, 0, as_stream(stream)>>>(sp, static_cast<LayerTab*>(tables));
+    loss_resize_setup_kernel<<<1, kSetupThreads, 0, as_stream(stream)>>>(sp, static_cast<uint32_t*>(tables));
     DH_LAUNCH_CHECK();
     return DH_OK;
 }
 
-int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags, int* ell_slices, int* ell_groups) {
-    DH_REQUIRE(plan_header_host);
+int dh_loss_plan_info(const void* plan_header_host, dh_loss_plan_desc* desc) {
+    DH_REQUIRE(plan_header_host && desc);
     const PlanHeader* h = static_cast<const PlanHeader*>(plan_header_host);
-    if (n_pairs) *n_pairs = h->n_pairs;
-    if (ell_slices) *ell_slices = h->n_slices;
-    if (ell_groups) *ell_groups = h->n_groups;
-    if (plan_flags) *plan_flags = h->reserved & 1;
-    if (box_cells) *box_cells = h->box_r1 >= h->box_r0 ? (h->box_r1 - h->box_r0 + 1) * (h->box_s1 - h->box_s0 + 1) : 0;
+    desc->n_pairs = h->n_pairs;
+    desc->flags = h->reserved & 1;
+    desc->box_cells = h->box_r1 >= h->box_r0 ? (h->box_r1 - h->box_r0 + 1) * (h->box_s1 - h->box_s0 + 1) : 0;
+    desc->ell_slices = h->n_slices;
+    desc->ell_groups = h->n_groups;
+    desc->n_src_cells = h->n_usrc;
     return DH_OK;
 }
 
-int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan, int n_fg, int n_bg_orig,
-                     int n_bg_trans, int n_bg_common, int box_cells, int plan_flags, int ell_slices, int ell_groups, int fg_kind,
-                     int bg_kind, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan, const dh_loss_plan_desc* desc,
+                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind, float* loss_out,
+                     void* ws, size_t ws_bytes, void* stream) {
+    DH_REQUIRE(desc);
+    const int plan_flags = desc->flags, ell_slices = desc->ell_slices, ell_groups = desc->ell_groups;
     DH_REQUIRE(layers_host && n_layers >= 1 && n_layers <= kMaxLossLayers && loss_out && ws && plan);
     DH_REQUIRE(grid >= 1 && grid <= kMaxG);
     DH_REQUIRE(n_fg >= 0 && n_bg_orig >= 0 && n_bg_trans >= 0 && n_bg_common >= 0);
@@ -1082,7 +1106,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     FusedParams fp;
     memset(&fp, 0, sizeof(fp));
     const int GG = grid * grid;
-    int chan = 0, h_r = 0, wrow_floats = 0, wcol_floats = 0;
+    int chan = 0, first_small = -1, n_small_layers = 0;
     for (int i = 0; i < n_layers; ++i) {
         const dh_loss_layer& s = layers_host[i];
         DH_REQUIRE(s.cur && s.orig && s.channels >= 1 && s.h >= 1 && s.w >= 1);
@@ -1113,13 +1137,9 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
             L.ppi = ppi;
             L.item_begin = fp.n_small_items;
             fp.n_small_items += (s.channels + ppi - 1) / ppi;
-            if (s.h > h_r) h_r = s.h;
-            // rows of the transposed-resize tables in shared memory: at most 2 * ceil(grid / h) up rows touch one native row
-            const int wy = 2 * ((grid + s.h - 1) / s.h) < kWin ? 2 * ((grid + s.h - 1) / s.h) : kWin;
-            const int wx = 2 * ((grid + s.w - 1) / s.w) < kWin ? 2 * ((grid + s.w - 1) / s.w) : kWin;
-            const int wmax = wy > wx ? wy : wx;       // the tables share one stride
-            if (s.h * wmax > wrow_floats) wrow_floats = s.h * wmax;
-            if (s.w * wmax > wcol_floats) wcol_floats = s.w * wmax;
+            if (bg_kind == 2) return DH_ERR_UNSUPPORTED;      // 'local_avg' on a resized layer: dh_guidance_loss_patch (patch 1)
+            if (first_small < 0) first_small = i;
+            ++n_small_layers;
         }
     }
     fp.n_layers = n_layers;
@@ -1137,32 +1157,26 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         const char* e = getenv("DH_LOSS_DEBUG_BUF");      // developer aid: address of a device buffer of 4 * grid u64
         fp.debug = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
     }
-    // scratch: the tables of the current resized layer, then the per-plane buffers of a resized plane overlaid with the
-    // sign-count buffer of a flat plane
+    // scratch of a group: the slot arrays of a resized plane pair, overlaid with the sign counts of a flat plane
     auto up4 = [](int v) { return (v + 3) / 4 * 4; };
     ResizeLayout& lay = fp.lay;
     int o = 0;
     if (fp.n_small_items) {
-        int cap = (box_cells > 0 && box_cells <= GG && bg_kind != 2) ? box_cells : GG;
-        if (!fg_kind && bg_kind != 2) cap = 4;
-        lay.tab = o;    o += (int)(sizeof(LayerTabHead) / 4);
-        lay.wrow = o;   o += up4(wrow_floats);
-        lay.wcol = o;   o += up4(wcol_floats);
-        // two planes at a time: float2 per box cell.  tmp (2 * h * grid floats) is written when uc / uo are dead
-        const int plane_area = 4 * up4(cap) > 2 * up4(h_r * grid) ? 4 * up4(cap) : 2 * up4(h_r * grid);
-        lay.uc = o;     lay.uo = o + 2 * up4(cap);  lay.tmp = o;   o += plane_area;
-        lay.cnt = o;    o += 2 * up4(cap);
-        lay.box_cap = cap;
+        const int n_src = fg_kind ? (desc->n_src_cells > 0 ? desc->n_src_cells : GG) : 0;
+        const int n_slots = fg_kind ? (ell_slices > 0 ? ell_slices * 32 : GG) : 0;
+        lay.cap_usrc = n_src; lay.cap_slots = n_slots;
+        lay.uo = o; o += up4(2 * n_src);
+        lay.uc = o; o += up4(2 * n_slots);
+        lay.gs = o; o += up4(2 * n_slots);
     }
-    lay.flat_cnt = fp.n_small_items ? lay.uc : 0;
-    if (fp.n_flat_items && lay.flat_cnt + GG > o) o = lay.flat_cnt + GG;
+    if (fp.n_flat_items && GG > o) o = GG;
     lay.total = o;
-    fp.scratch_floats = up4(o);
+    fp.scratch_floats = (up4(o) + 31) / 32 * 32;      // (groups stay 128-byte aligned)
     cudaStream_t st = as_stream(stream);
     // per-process caches of the launch geometry queries (this entry point runs every denoising step)
     struct LaunchCache {
         int sms, max_smem;
-        size_t smem_attr_set[4];
+        size_t smem_attr_set[8];
     };
     static LaunchCache caches[64];          // zero-initialised; one entry per device (function attributes are per device)
     int dev = 0;
@@ -1187,26 +1201,53 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         ell_words = up4(fp.ell_ent_at + fp.ell_ent_cap);
         ell_words = (ell_words + 31) / 32 * 32;        // the groups' stages stay 128-byte aligned
     }
-    int groups = 0;
-    if (ell_words && sizeof(float) * ell_words + 2 * group_bytes <= budget) {
-        groups = sizeof(float) * ell_words + 3 * group_bytes <= budget ? 3 : 2;
-        fp.ell_floats = ell_words;
-    } else {
-        fp.ell_floats = 0;
-        for (groups = kMaxGroups; groups > 1 && groups * group_bytes > budget; --groups) {}
+    // table blob of the first resized layer: its exact size is on the device; budget for the largest it can be given the plan
+    int tab_words = 0;
+    if (first_small >= 0) {
+        const dh_loss_layer& sl = layers_host[first_small];
+        const int n_src = fg_kind ? (desc->n_src_cells > 0 ? desc->n_src_cells : GG) : 0;
+        const int n_slots = fg_kind ? (ell_slices > 0 ? ell_slices * 32 : GG) : 0;
+        const int n_rows_max = n_slots;
+        tab_words = 16 + 4 * n_src + 4 * n_slots + up4(sl.h * sl.w + 1) + up4(2 * (4 * n_rows_max + 3 * sl.h * sl.w));      // (everything in front of wo / wt; native lists padded to 4)
+        tab_words = (tab_words + 31) / 32 * 32;
     }
+    // preference: three groups with the plan and the tables in shared memory, then without the tables, then two groups ...
+    // (the tables of ONE resized layer fit; with several resized layers they all stay in global memory)
+    int groups = 0, mem = 0;
+    fp.ell_floats = 0; fp.tab_floats = 0; fp.tab_layer = first_small >= 0 ? first_small : 0;
+    const size_t ellb = sizeof(float) * ell_words, tabb = sizeof(float) * tab_words;
+    const bool tab_ok = n_small_layers == 1 && tab_words > 0 && grid == 64;
+    for (int g = kMaxGroups; g >= 1 && !groups; --g) {
+        if (ell_words && tab_ok && ellb + tabb + g * group_bytes <= budget) { groups = g; mem = 2; }
+        else if (ell_words && grid == 64 && ellb + g * group_bytes <= budget && g >= 2) { groups = g; mem = 1; }
+        else if (g * group_bytes <= budget && (g >= 2 || !ell_words)) { groups = g; mem = 0; }
+    }
+    if (!groups) {
+        if (group_bytes > budget) return DH_ERR_UNSUPPORTED;
+        groups = 1;
+    }
+    {
+        const char* e = getenv("DH_LOSS_MEM");       // developer knob: cap the shared-memory placement (0, 1, 2)
+        if (e && atoi(e) >= 0 && atoi(e) < mem) mem = atoi(e);
+    }
+    if (mem >= 1) fp.ell_floats = ell_words;
+    if (mem == 2) fp.tab_floats = tab_words;
     const int n_items = fp.n_flat_items + fp.n_small_items;
     {
         const char* e = getenv("DH_LOSS_GROUPS");       // developer knob
         if (e && atoi(e) >= 1 && atoi(e) < groups) groups = atoi(e);
     }
     while (groups > 1 && lc.sms * (groups - 1) >= n_items) --groups;      // tiny problems: no idle groups
-    const size_t smem = sizeof(float) * fp.ell_floats + groups * group_bytes;
+    const size_t smem = sizeof(float) * ((size_t)fp.ell_floats + fp.tab_floats) + groups * group_bytes;
     if (smem > budget + static_bytes) return DH_ERR_UNSUPPORTED;
     // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
-    const int vi = (grid == 64 ? 2 : 0) + ((plan_flags & 1) ? 1 : 0);
-    void (*kernel)(const FusedParams) = vi == 3 ? loss_fused_kernel<64, true> : vi == 2 ? loss_fused_kernel<64, false>
-                                        : vi == 1 ? loss_fused_kernel<0, true> : loss_fused_kernel<0, false>;
+    // (shared-memory placement is only instantiated for the reference's 64 x 64 grid)
+    const int vi = grid == 64 ? 2 + 2 * mem + ((plan_flags & 1) ? 1 : 0) : ((plan_flags & 1) ? 1 : 0);
+    void (*kernel)(const FusedParams) =
+        vi == 0 ? loss_fused_kernel<0, false, 0> : vi == 1 ? loss_fused_kernel<0, true, 0>
+        : vi == 2 ? loss_fused_kernel<64, false, 0> : vi == 3 ? loss_fused_kernel<64, true, 0>
+        : vi == 4 ? loss_fused_kernel<64, false, 1> : vi == 5 ? loss_fused_kernel<64, true, 1>
+        : vi == 6 ? loss_fused_kernel<64, false, 2> : loss_fused_kernel<64, true, 2>;
     if (smem > lc.smem_attr_set[vi]) {
         DH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lc.smem_attr_set[vi] = smem;

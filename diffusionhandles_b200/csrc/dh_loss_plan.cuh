@@ -11,7 +11,7 @@ constexpr int kMaxNative = 64;
 struct PlanHeader {
     int32_t n_pairs, n_fg, n_bg_orig, n_bg_trans, n_bg_common, grid, cap, reserved;
     int32_t box_r0, box_r1, box_s0, box_s1;   // box (loss-grid rows / columns) of the cells that are a pair source or destination
-    int32_t n_rows, n_slices, n_groups, pad;  // sliced-ELL view of the pairs (below)
+    int32_t n_rows, n_slices, n_groups, n_usrc;  // sliced-ELL view of the pairs (below); number of distinct source cells
 };
 static_assert(sizeof(PlanHeader) == 64, "the host reads the first 64 bytes of a plan");
 
@@ -24,24 +24,23 @@ struct PlanView {
     PlanHeader* hdr;
     int32_t* row_ptr;      // cells + 1
     ushort4* bgcnt;        // cells: (count in bg_orig, bg_trans, bg_common, bit0 = cell is the source of a pair)
-    uint2* pairs;          // cap entries: x = src | dst << 16, y = multiplicity
+    uint2* pairs;          // cap entries: x = src | dst << 16, y = multiplicity (<= 255; larger ones are split)
     int32_t* ell_off;      // slices + 1: first 32-entry group of every slice
     uint32_t* row_desc;    // 32 per slice: dst cell | len << 16 (len = 0: no row)
-    uint32_t* ent;         // 32 per group: src cell | multiplicity << 12 (multiplicity <= 65535)
-    uint32_t* row_desc_box;   // the same with cell ids local to the box of pair cells: (r - box_r0) * box_w + (s - box_s0)
-    uint32_t* ent_box;
+    uint32_t* ent;         // 32 per group: src cell | src slot << 12 | multiplicity << 24 (multiplicity <= 255; slot = index in usrc_cell)
+    uint16_t* usrc_cell;   // cells: the distinct source cells, ascending (resized layers up-sample one value per slot)
     uint2* own_masks;      // 256: per thread of the loss kernel, membership bits of its 16 own cells (see loss_fused_kernel)
 };
 
 __host__ __device__ inline size_t plan_ent_cap(int grid, int cap) {
     const size_t cells = (size_t)grid * grid, n = cap > 0 ? (size_t)cap : 1;
     // sum over slices of 32 * (longest row of the slice) <= n_pairs + 32 * (longest row of all); a row has at most one entry
-    // per source cell plus the entries that a multiplicity > 65535 is split into
+    // per source cell plus the entries that a multiplicity > 255 is split into
     // (+ the padding of every row to a multiple of four entries: at most 3 * 32 per slice)
-    return n + 32 * ((n < cells ? n : cells) + (n >> 16) + 1) + 96 * ((cells + 31) / 32);
+    return n + 32 * ((n < cells ? n : cells) + (n >> 8) + 1) + 96 * ((cells + 31) / 32);
 }
 
-struct PlanOffsets { size_t row, bg, pairs, ell_off, row_desc, ent, row_desc_box, ent_box, own_masks, total; };
+struct PlanOffsets { size_t row, bg, pairs, ell_off, row_desc, ent, usrc_cell, own_masks, total; };
 
 __host__ __device__ inline PlanOffsets plan_layout(int grid, int cap) {
     const size_t cells = (size_t)grid * grid, slices = (cells + 31) / 32;
@@ -53,8 +52,7 @@ __host__ __device__ inline PlanOffsets plan_layout(int grid, int cap) {
     L.ell_off = o;  o += ((slices + 1) * sizeof(int32_t) + 15) / 16 * 16;
     L.row_desc = o; o += slices * 32 * sizeof(uint32_t);
     L.ent = o;      o += (plan_ent_cap(grid, cap) * sizeof(uint32_t) + 15) / 16 * 16;
-    L.row_desc_box = o; o += slices * 32 * sizeof(uint32_t);
-    L.ent_box = o;  o += (plan_ent_cap(grid, cap) * sizeof(uint32_t) + 15) / 16 * 16;
+    L.usrc_cell = o; o += (cells * sizeof(uint16_t) + 15) / 16 * 16;
     L.own_masks = o; o += 256 * sizeof(uint2);
     L.total = o;
     return L;
@@ -71,8 +69,7 @@ __host__ __device__ inline PlanView plan_view(void* plan, int grid, int cap) {
     v.ell_off = reinterpret_cast<int32_t*>(p + L.ell_off);
     v.row_desc = reinterpret_cast<uint32_t*>(p + L.row_desc);
     v.ent = reinterpret_cast<uint32_t*>(p + L.ent);
-    v.row_desc_box = reinterpret_cast<uint32_t*>(p + L.row_desc_box);
-    v.ent_box = reinterpret_cast<uint32_t*>(p + L.ent_box);
+    v.usrc_cell = reinterpret_cast<uint16_t*>(p + L.usrc_cell);
     v.own_masks = reinterpret_cast<uint2*>(p + L.own_masks);
     return v;
 }

@@ -68,11 +68,9 @@ class LossPlan:
                                        N.stream_handle(torch.device(device))), "dh_build_loss_plan")
         # one small read-back per edit: the plan header tells how big the box-local buffers of the kernel must be
         hdr = self.buf[:64].cpu().numpy().tobytes()
-        n_pairs, box, flags, slices, groups = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
-        N.check(lib.dh_loss_plan_info(hdr, C.byref(n_pairs), C.byref(box), C.byref(flags), C.byref(slices), C.byref(groups)),
-                "dh_loss_plan_info")
-        self.n_pairs, self.box_cells, self.flags = n_pairs.value, box.value, flags.value
-        self.ell_slices, self.ell_groups = slices.value, groups.value
+        self.desc = N.dh_loss_plan_desc()
+        N.check(lib.dh_loss_plan_info(hdr, C.byref(self.desc)), "dh_loss_plan_info")
+        self.n_pairs, self.box_cells, self.flags = self.desc.n_pairs, self.desc.box_cells, self.desc.flags
         self._tables = {}
         self._runners = {}
 
@@ -120,7 +118,9 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
     L = len(curs)
     shapes = tuple(tuple(c.shape) for c in curs)
     # maps smaller than grid/8 (e.g. 4x4) exceed the tap window of the specialised patch-1 kernels: the general kernel takes them
-    general = patch != 1 or any(2 * -(-plan.grid // min(sh[1], sh[2])) > 16 for sh in shapes)
+    # 'local_avg' on a layer smaller than the grid needs the whole up-sampled map: the general kernel takes it (no shipped config does)
+    general = (patch != 1 or any(2 * -(-plan.grid // min(sh[1], sh[2])) > 16 for sh in shapes)
+               or (bg_kind == _BG_LOCAL and any((sh[1], sh[2]) != (plan.grid, plan.grid) for sh in shapes)))
     key = (shapes, fg_kind, bg_kind, patch, general)
     runner = plan._runners.get(key)
     if runner is None:
@@ -160,8 +160,7 @@ def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_gr
     n_fg, n_bo, n_bt, n_bc = plan.n
     st = N.stream_handle(dev)
     if not general:
-        N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, plan.box_cells, plan.flags,
-                                     plan.ell_slices, plan.ell_groups, fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
+        N.check(lib.dh_guidance_loss(layers, L, plan.grid, plan.buf.data_ptr(), C.byref(plan.desc), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind, out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss")
     else:
         N.check(lib.dh_guidance_loss_patch(layers, L, plan.grid, patch, plan.buf.data_ptr(), n_fg, n_bo, n_bt, n_bc, fg_kind, bg_kind,
                                            out.data_ptr(), ws.data_ptr(), ws_bytes, st), "dh_guidance_loss_patch")

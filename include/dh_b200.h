@@ -246,18 +246,22 @@ int dh_build_loss_resize_tables(const void* plan, int n_fg, int grid, int h, int
                                 void* tables, void* stream);
 
 size_t dh_guidance_loss_workspace_bytes(int n_layers, int max_channels);
-/* Reads a HOST copy of the first 64 bytes of a plan: number of distinct pairs and the size (cells) of the box that
- * contains every pair cell.  box_cells sizes the shared-memory buffers of the resized layers (0 = assume the whole grid);
- * plan_flags bit 0 = every background multiplicity is 0 or 1 (selects the bit-mask instantiation; 0 is always safe);
- * ell_slices / ell_groups = size of the plan's sliced-ELL pair table (sizes its shared-memory copy; 0 = read it from global). */
-int dh_loss_plan_info(const void* plan_header_host, int* n_pairs, int* box_cells, int* plan_flags, int* ell_slices,
-                      int* ell_groups);
+/* What the launcher needs to know about a plan; filled from a HOST copy of the first 64 bytes of the plan. */
+typedef struct dh_loss_plan_desc {
+    int32_t n_pairs;       /* distinct (src, dst) cell pairs                                                     */
+    int32_t box_cells;     /* cells of the box that contains every pair cell                                      */
+    int32_t flags;         /* bit 0: every background multiplicity is 0 or 1 (bit-mask instantiation)             */
+    int32_t ell_slices;    /* size of the sliced-ELL pair table: slices of 32 destination rows ...                */
+    int32_t ell_groups;    /* ... and groups of 32 entries (sizes its shared-memory copy)                         */
+    int32_t n_src_cells;   /* distinct source cells (sizes the per-plane buffers of the resized layers)           */
+} dh_loss_plan_desc;
+int dh_loss_plan_info(const void* plan_header_host, dh_loss_plan_desc* desc);
 /* n_* are the list lengths the plan was built from (they are the means' denominators).  ONE persistent launch for all
  * layers.  `ws` must be zero-filled once before its first use; the launch leaves its queue counters zeroed again, so the
- * same workspace serves every following evaluation without a memset (one evaluation at a time per workspace). */
-int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan,
-                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int box_cells, int plan_flags,
-                     int ell_slices, int ell_groups, int fg_kind, int bg_kind,
+ * same workspace serves every following evaluation without a memset (one evaluation at a time per workspace).
+ * 'local_avg' background terms on layers smaller than the grid are DH_ERR_UNSUPPORTED here: use dh_guidance_loss_patch. */
+int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, const void* plan, const dh_loss_plan_desc* desc,
+                     int n_fg, int n_bg_orig, int n_bg_trans, int n_bg_common, int fg_kind, int bg_kind,
                      float* loss_out /* device float[1 + 2*n_layers]: total, then fg_l, bg_l */,
                      void* ws, size_t ws_bytes, void* stream);
 /* The same losses with patch_size > 1 (losses.py:62-77: both maps are replaced by their local averages over the indexed

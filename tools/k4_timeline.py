@@ -40,7 +40,7 @@ v = np.array(list(per_sm.values()))
 print(f"SMs {len(v)}: last CTA end per SM: min {v.min():.1f} med {np.median(v):.1f} max {v.max():.1f}")
 
 if ph.any():
-    names = ["loop_top+wait_tma", "flat_item", "small_top+upsample", "small_rows+bg", "small_reduce", "small_gu+pass1", "prologue", "small_pass2"]
+    names = ["loop_top+wait_tma", "flat_item", "small_upsample+bg", "small_rows", "small_reduce", "small_stage_next", "prologue", "small_grad_gather"]
     tot = ph.sum(0)
     print("thread-0 cycles by phase (sum over CTAs, share):")
     for n, v in zip(names, tot):
