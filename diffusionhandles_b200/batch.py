@@ -75,29 +75,56 @@ class EditWarpPipeline:
             )
             self.slots.append(slot)
         self.launches_per_chunk = 4 + 2 + 2 + 4 + 2 + 1 + 2 * len(self.level_shapes) + 1
+        self._table = None
 
-    def h2d_bytes_per_edit(self) -> int:
-        return 3 * self.S * self.S * 4 + sum(c * s * s * 4 for c, s in self.level_shapes)
+    def h2d_bytes_per_edit(self, edits_per_scene: float = 1.0) -> float:
+        """depth + bg + mask (shared by the `edits_per_scene` edits of a scene when a scene table is used) + the stack."""
+        return 3 * self.S * self.S * 4 / edits_per_scene + sum(c * s * s * 4 for c, s in self.level_shapes)
 
     def d2h_bytes_per_edit(self) -> int:
         return sum(c * s * s * 4 for c, s in self.level_shapes) + 4
 
     def run_host(self, depth_h: torch.Tensor, bg_h: torch.Tensor, mask_h: torch.Tensor, intrinsics: torch.Tensor,
                  rigids: Sequence[N.dh_rigid], levels_h: Sequence[torch.Tensor], outs_h: Sequence[torch.Tensor],
-                 n_corr_h: torch.Tensor) -> None:
-        """All *_h tensors are pinned host tensors with a leading edit dimension E (E % chunk == 0).
-        On return (after a final synchronisation) outs_h / n_corr_h hold the results."""
-        E = depth_h.shape[0]
+                 n_corr_h: torch.Tensor, scene_index: Optional[Sequence[int]] = None) -> None:
+        """All *_h tensors are pinned host tensors.  levels_h / outs_h / n_corr_h have a leading edit dimension E
+        (E % chunk == 0).  Without ``scene_index`` depth_h / bg_h / mask_h are per EDIT (E,S,S).  With ``scene_index``
+        (E ints) they are a SCENE TABLE (n_scenes,S,S): an edit sweep is typically a few scenes x many transforms, so every
+        depth / background / mask crosses PCIe once per scene instead of once per edit and the edits pick their scene on the
+        device.  On return (after a final synchronisation) outs_h / n_corr_h hold the results."""
+        E = levels_h[0].shape[0]
         if E % self.chunk:
             raise ValueError(f"number of edits {E} must be a multiple of the chunk size {self.chunk}")
         sides = [s for _, s in self.level_shapes]
+        table = None
+        if scene_index is not None:
+            if len(scene_index) != E:
+                raise ValueError("scene_index needs one entry per edit")
+            n_scenes = depth_h.shape[0]
+            if self._table is None or self._table[0].shape[0] < n_scenes:
+                self._table = tuple(torch.empty((n_scenes, self.S, self.S), dtype=torch.float32, device=self.device) for _ in range(3))
+                self._table_ready = torch.cuda.Event()
+            up = self.slots[0]["stream"]
+            with torch.cuda.stream(up):
+                for d, h in zip(self._table, (depth_h, bg_h, mask_h)):
+                    d[:n_scenes].copy_(h, non_blocking=True)
+                self._table_ready.record(up)
+            table = self._table
+            idx_all = torch.as_tensor(list(scene_index), dtype=torch.int64).pin_memory()
         for ci, e0 in enumerate(range(0, E, self.chunk)):
             slot = self.slots[ci % len(self.slots)]
             e1 = e0 + self.chunk
             with torch.cuda.stream(slot["stream"]):
-                slot["depth"].copy_(depth_h[e0:e1], non_blocking=True)
-                slot["bg"].copy_(bg_h[e0:e1], non_blocking=True)
-                slot["mask"].copy_(mask_h[e0:e1], non_blocking=True)
+                if table is None:
+                    slot["depth"].copy_(depth_h[e0:e1], non_blocking=True)
+                    slot["bg"].copy_(bg_h[e0:e1], non_blocking=True)
+                    slot["mask"].copy_(mask_h[e0:e1], non_blocking=True)
+                else:
+                    slot["stream"].wait_event(self._table_ready)
+                    idx = idx_all[e0:e1].to(self.device, non_blocking=True)
+                    torch.index_select(table[0], 0, idx, out=slot["depth"])
+                    torch.index_select(table[1], 0, idx, out=slot["bg"])
+                    torch.index_select(table[2], 0, idx, out=slot["mask"])
                 for d, h in zip(slot["levels"], levels_h):
                     d.copy_(h[e0:e1], non_blocking=True)
                 eng: EditEngine = slot["engine"]
@@ -111,6 +138,75 @@ class EditWarpPipeline:
                 n_corr_h[e0:e1].copy_(res.n_corr, non_blocking=True)
         for slot in self.slots:
             slot["stream"].synchronize()
+
+
+class DeviceSweep:
+    """A sweep of independent edits whose inputs (depths, masks, transforms, activation stacks) are RESIDENT on one GPU:
+    K1 -> K2 -> masks -> correspondences -> dense maps -> K3 per chunk, all on the current stream.  The launch chain of a
+    chunk (~25 launches) is captured once in a CUDA graph and replayed, so that a small shard (a strong-scaling run leaves 32
+    edits per GPU at 8 GPUs) is not bound by host launch overhead.  This is the per-rank body of BASELINE config 4."""
+
+    def __init__(self, device: torch.device, S: int, level_shapes: Sequence[Tuple[int, int]], depth: torch.Tensor, bg: torch.Tensor,
+                 mask: torch.Tensor, intrinsics: torch.Tensor, rigids: Sequence[N.dh_rigid], levels: Sequence[torch.Tensor],
+                 chunk: Optional[int] = None, use_graph: bool = True, full_winner_map: bool = True):
+        self.device = torch.device(device)
+        E = depth.shape[0]
+        self.E, self.S = E, S
+        self.chunk = chunk or E
+        if E % self.chunk:
+            raise ValueError(f"number of edits {E} must be a multiple of the chunk size {self.chunk}")
+        self.sides = [s for _, s in level_shapes]
+        self.depth, self.bg, self.mask, self.K, self.rigids, self.levels = depth, bg, mask, intrinsics, list(rigids), list(levels)
+        self.outs = [torch.empty_like(l) for l in levels]
+        self.n_corr = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.full_winner_map = full_winner_map
+        # one engine (scratch) per chunk position when graphs are used: a captured chain is bound to its buffers
+        n_chunks = E // self.chunk
+        self.engines = [EditEngine(self.device, self.chunk, S, S) for _ in range(n_chunks if use_graph else 1)]
+        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * n_chunks
+        self.use_graph = use_graph
+        self.launches_per_chunk = 25
+
+    def _chunk(self, ci: int):
+        e0, e1 = ci * self.chunk, (ci + 1) * self.chunk
+        eng = self.engines[ci if self.use_graph else 0]
+        res = eng.run(self.depth[e0:e1], self.bg[e0:e1], self.mask[e0:e1], self.K, self.rigids[e0:e1], poisson=False,
+                      sync_counts=False)
+        maps = warp.dense_source_maps(res.corr, res.n_corr, self.S, self.sides, res.winner_src if self.full_winner_map else None)
+        warp.warp_stacks([l[e0:e1] for l in self.levels], maps, [o[e0:e1] for o in self.outs])
+        self.n_corr[e0:e1].copy_(res.n_corr)
+
+    def capture(self):
+        """Warm up every chunk once, then capture it (idempotent)."""
+        if not self.use_graph or all(g is not None for g in self.graphs):
+            return
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for ci in range(len(self.graphs)):
+                self._chunk(ci)
+            side.synchronize()
+            for ci in range(len(self.graphs)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._chunk(ci)
+                self.graphs[ci] = g
+        torch.cuda.current_stream(self.device).wait_stream(side)
+
+    def run(self):
+        """Enqueue the whole sweep on the current stream (no synchronisation)."""
+        if self.use_graph:
+            self.capture()
+            for g in self.graphs:
+                g.replay()
+        else:
+            for ci in range(len(self.graphs)):
+                self._chunk(ci)
+
+    def records(self) -> torch.Tensor:
+        """Fixed-size per-edit result records (n_corr, 64-bit checksum of the first warped level) for the result gather."""
+        chk = self.outs[-1].flatten(1).view(torch.int32).sum(1, dtype=torch.int64)      # (the smallest level: cheap)
+        return torch.stack([self.n_corr.to(torch.int64), chk], dim=1).contiguous()
 
 
 def gather_records(records: torch.Tensor, dst: int = 0):
