@@ -420,6 +420,15 @@ def variant_strong_scaling(dev, rank, world, steps=5):
     chunk = n_local if n_local <= 64 else 64
     sweep = DeviceSweep(dev, S, LEVELS, depth, bg, mask, K, rigids, levels, chunk=chunk, use_graph=True)
     sweep.capture()
+    # the replayed graphs must give what the plain launch chain gives (first chunk: counts and the warped stack)
+    sweep.run()
+    ref = DeviceSweep(dev, S, LEVELS, depth[:chunk], bg[:chunk], mask[:chunk], K, rigids[:chunk], [l[:chunk] for l in levels],
+                      chunk=chunk, use_graph=False)
+    ref.run()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(sweep.n_corr[:chunk], ref.n_corr) and int(ref.n_corr.sum()) > 0, "graph replay differs from the plain launch chain"
+    assert all(torch.equal(a[:chunk], b) for a, b in zip(sweep.outs, ref.outs)), "graph replay: warped stacks differ"
+    del ref
 
     def step():
         sweep.run()

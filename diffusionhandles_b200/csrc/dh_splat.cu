@@ -196,11 +196,18 @@ inv_minmax_kernel(const float* __restrict__ depth, int P, float* __restrict__ ou
 __global__ void __launch_bounds__(256) disparity_kernel(const float* __restrict__ depth, int P, const float* __restrict__ bounds,
                                                         float* __restrict__ disp) {
     const int e = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
     const float mn = bounds[e * 2], mx = bounds[e * 2 + 1];
-    const float x = __fdiv_rn(1.0f, depth[(size_t)e * P + p]);
-    disp[(size_t)e * P + p] = __fdiv_rn(__fmul_rn(255.0f, __fsub_rn(x, mn)), __fsub_rn(mx, mn));
+    const float range = __fsub_rn(mx, mn);
+    const float* d = depth + (size_t)e * P;
+    float* o = disp + (size_t)e * P;
+    auto one = [&](float v) { return __fdiv_rn(__fmul_rn(255.0f, __fsub_rn(__fdiv_rn(1.0f, v), mn)), range); };
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;       // four pixels per thread: 128-bit loads and stores
+    if (p0 + 3 < P && ((((size_t)e * P) & 3) == 0) && ((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(disp)) & 15) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(d + p0));
+        *reinterpret_cast<float4*>(o + p0) = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
+    } else {
+        for (int p = p0; p < min(P, p0 + 4); ++p) o[p] = one(d[p]);
+    }
 }
 
 }  // namespace dh
@@ -274,7 +281,7 @@ int dh_inv_minmax(const float* depth, int B, int P, float* inv_minmax, void* str
 
 int dh_disparity(const float* depth, int B, int P, const float* bounds, float* disparity, void* stream) {
     DH_REQUIRE(depth && bounds && disparity && B >= 1 && P >= 1);
-    dim3 grid((P + 255) / 256, B);
+    dim3 grid((P + 1023) / 1024, B);
     disparity_kernel<<<grid, 256, 0, as_stream(stream)>>>(depth, P, bounds, disparity);
     DH_LAUNCH_CHECK();
     return DH_OK;

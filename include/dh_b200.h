@@ -130,6 +130,20 @@ int dh_unproject_transform_project_splat(const float* depth, const float* bg_dep
                                          float* centroid, double* points_out, uint64_t* zbuf,
                                          void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K1 + K2 of a batch of edits in one call (what transform_depth_pc runs, depth_transform.py:226-306) ----------
+ * Same results as dh_unproject_transform_project_splat + dh_splat_winner + dh_splat_resolve, bit for bit, in seven
+ * launches and without memsets: with the library's pinhole camera a background point provably keeps its pixel, so the
+ * z-buffer is initialised with the background keys (float4 loads, 128-bit stores), the fp64 transform / projection runs for
+ * the foreground points only, and a background pixel resolves itself.  Background depths that are zero, infinite or of absurd
+ * magnitude, and any camera / image outside that class, take the generic per-point path inside the same kernels.
+ * pix / zkey: (B, 2P) - filled for the foreground points (index P + j); the background half only when points_out != NULL
+ * (debug: the generic projection of every background point).  inv_minmax as in dh_splat_resolve (may be NULL). */
+int dh_edit_splat(const float* depth, const float* bg_depth, const float* fg_mask, int B, int H, int W,
+                  const dh_camera* cam_host, const dh_rigid* rigid_host, const float* xs, const float* ys,
+                  int32_t* pix, uint64_t* zkey, int32_t* fg_index, int32_t* n_fg, float* centroid, double* points_out,
+                  uint64_t* zbuf, uint32_t* winner, float* depth_map, uint8_t* target_mask, uint32_t* target_bits,
+                  int32_t* winner_src, float* inv_minmax, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K2, row 5: deterministic z-buffer splat, depth_transform.py:689-712 ---------------------------
  * winner[q] = argmin over {i : pix_i = q} of (z_i, i).  Two 64/32-bit atomicMin passes (z bits, then
  * point index among the points that tie on z) - exact for fp64 depths.

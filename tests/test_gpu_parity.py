@@ -1026,3 +1026,87 @@ def test_poisson_solve_large_system_uses_the_global_path(dev):
     ref = O.poisson_solve(img, mask)
     assert np.array_equal(out[~mask], img[~mask])
     assert np.abs(out - ref).max() <= 1e-3
+
+
+def test_device_sweep_graph_replay_matches_plain_launches(dev, K):
+    """The per-rank body of the strong-scaling sweep (BASELINE config 4): the CUDA-graph replay of a chunk's launch chain gives
+    exactly what the plain launches give, also after the engine has been used for other transforms (the transforms are re-read
+    from the engine's host array at every replay)."""
+    from diffusionhandles_b200.batch import DeviceSweep
+    from diffusionhandles_b200.engine import make_rigid
+    S, B = 128, 6
+    levels_shapes = [(8, 64), (16, 32), (32, 16), (32, 8)]
+    scenes = [O.synthetic_scene(S, 40 + i) for i in range(B)]
+    depth, bg, mask = (torch.from_numpy(np.stack([s[k] for s in scenes])).to(dev) for k in range(3))
+    rigids = [make_rigid(10.0 * i - 25.0, [0.0, 1.0, 0.0], [0.05 * i, 0.0, 0.02 * i]) for i in range(B)]
+    g = torch.Generator(device=dev).manual_seed(9)
+    levels = [torch.randn((B, c, s, s), generator=g, device=dev) for c, s in levels_shapes]
+    Kc = K.cpu()
+    plain = DeviceSweep(dev, S, levels_shapes, depth, bg, mask, Kc, rigids, levels, chunk=3, use_graph=False)
+    graph = DeviceSweep(dev, S, levels_shapes, depth, bg, mask, Kc, rigids, levels, chunk=3, use_graph=True)
+    plain.run()
+    for _ in range(3):
+        graph.run()
+    torch.cuda.synchronize(dev)
+    assert int(plain.n_corr.sum()) > 0 and torch.equal(plain.n_corr, graph.n_corr)
+    for a, b in zip(plain.outs, graph.outs):
+        assert torch.equal(a, b)
+    assert torch.equal(plain.records(), graph.records())
+    # against the oracle too (edit 4)
+    o = O.transform_depth_pc(scenes[4][0], scenes[4][1], scenes[4][2], K_NP, 10.0 * 4 - 25.0, (0, 1, 0), f32_translation((0.2, 0.0, 0.08)),
+                             poisson=False)
+    assert int(graph.n_corr[4]) == o["correspondences"].shape[0]
+
+
+@pytest.mark.parametrize("H,W", [(128, 128), (96, 160)])
+def test_edit_fast_splat_equals_all_points_formulation(dev, K, H, W):
+    """dh_edit_splat (background pixels resolve themselves, generic path for foreground + odd points) against the all-points
+    formulation (dh_unproject_transform_project_splat + dh_splat_winner + dh_splat_resolve), bit for bit: regular scenes, background
+    depths that are zero / infinite / NaN / subnormal / negative / huge, exact z ties between background and foreground, a
+    non-square image (no pixel-keeping guarantee: every background point takes the generic path), with and without the debug outputs."""
+    from diffusionhandles_b200.engine import EditEngine, make_rigid
+    rng = np.random.default_rng(5)
+    B = 4
+    S = max(H, W)
+    scenes = [O.synthetic_scene(S, 60 + i, quantize=0.1 if i == 1 else None) for i in range(B)]
+    depth = np.stack([s[0][:H, :W] for s in scenes]).copy()
+    bg = np.stack([s[1][:H, :W] for s in scenes]).copy()
+    mask = np.stack([s[2][:H, :W] for s in scenes]).copy()
+    odd = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3e35, -2.5, 1e-33], np.float32)
+    for e in (2, 3):                               # sprinkle odd background depths (and a few odd foreground depths)
+        idx = rng.choice(H * W, 400, replace=False)
+        bg[e].reshape(-1)[idx] = odd[rng.integers(0, len(odd), 400)]
+        jdx = rng.choice(H * W, 40, replace=False)      # (finite odd foreground depths: a NaN / inf would poison the centroid)
+        depth[e].reshape(-1)[jdx] = np.array([0.0, -0.0, 1e-42, -2.5, 1e-33], np.float32)[rng.integers(0, 5, 40)]
+    bg[3, :8] = 0.0                                # whole rows of zeros: thousands of points on one pixel
+    rig = [make_rigid(20.0 * i - 30.0, [0.0, 1.0, 0.0], [0.1 * i, 0.0, 0.05 * i]) for i in range(B)]
+    td, tb, tm = (torch.from_numpy(a).to(dev) for a in (depth, bg, mask))
+    Kc = K.cpu()
+    out = {}
+    for fast, keep in ((False, True), (True, True), (True, False)):
+        eng = EditEngine(dev, B, H, W, keep_points=keep)
+        eng.fast_splat = fast
+        res = eng.run(td, tb, tm, Kc, rig, poisson=False)
+        out[(fast, keep)] = {k: getattr(res, k).clone() for k in ("winner", "winner_src", "depth_map", "target_mask", "target_bits",
+                                                                 "cleaned_bits", "disparity_raw", "n_corr", "n_fg", "centroid")}
+        out[(fast, keep)]["corr"] = [res.correspondences(e).clone() for e in range(B)]
+        if keep:
+            n = [H * W + int(v) for v in res.n_fg_host]
+            out[(fast, keep)]["pix"] = [res.pix[e, :n[e]].clone() for e in range(B)]
+            out[(fast, keep)]["zkey"] = [res.zkey[e, :n[e]].clone() for e in range(B)]
+            out[(fast, keep)]["points"] = [res.points[e, :n[e]].clone() for e in range(B)]
+    ref = out[(False, True)]
+    assert int(ref["n_corr"].sum()) > 0
+    for key in ((True, True), (True, False)):
+        got = out[key]
+        for k in ("winner", "winner_src", "target_mask", "target_bits", "cleaned_bits", "n_corr", "n_fg"):
+            assert torch.equal(got[k], ref[k]), (key, k)
+        for k in ("depth_map", "disparity_raw", "centroid"):       # (NaN-safe: compare bit patterns)
+            assert torch.equal(got[k].view(torch.int32), ref[k].view(torch.int32)), (key, k)
+        for a, b in zip(got["corr"], ref["corr"]):
+            assert torch.equal(a, b)
+    for k in ("pix", "zkey"):
+        for a, b in zip(out[(True, True)][k], ref[k]):
+            assert torch.equal(a, b), k
+    for a, b in zip(out[(True, True)]["points"], ref["points"]):
+        assert torch.equal(a.view(torch.int64), b.view(torch.int64))
