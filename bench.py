@@ -315,6 +315,27 @@ def variant_single_edits(dev, with_cpu: bool):
     return out
 
 
+def variant_set_foreground(dev):
+    """DiffusionHandles.set_foreground at the real size (diffusion_handles.py:88-110; the reference's SuperLU solve takes 0.5-1.8 s
+    on the bundled scenes): config-1 scene, 15 px dilated mask, fp64 CG on the device."""
+    from diffusionhandles_b200.diffusion_handles import DiffusionHandles
+    from diffusionhandles_b200 import depth_transform as dt
+    from diffusionhandles_b200.synthetic import synthetic_scene
+    depth, bg, mask = synthetic_scene(512, 0)
+    td, tb, tm = (torch.from_numpy(a).to(dev)[None, None] for a in (depth, bg, mask))
+    dh = DiffusionHandles()
+    out = dh.set_foreground(td, tm, tb)
+    iters = int(dt._poisson_device.last_iters[0])
+    n_unknown = int((out[0, 0] != td[0, 0]).sum().item())
+    t0 = time.perf_counter()
+    for _ in range(5):
+        dh.set_foreground(td, tm, tb)
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / 5 * 1e3
+    return {"set_foreground_512": {"unknowns_approx": n_unknown, "cg_iterations": iters, "converged": iters > 0, "wall_ms": wall,
+                                   "reference": "scipy SuperLU on the CPU: 0.5-1.8 s per bundled scene (tests/golden/photogen_ref.json)"}}
+
+
 def variant_guidance_loss(dev):
     """BASELINE config 3: guidance loss forward + backward on the recorded-stack shapes for the 50 recorded timesteps.
     kernels: 50 evaluations (one per timestep, 3.1 GB of distinct inputs -> L2-cold) captured in one CUDA graph;
@@ -650,6 +671,7 @@ def run_ours(args):
         if world == 1:
             variants.update(variant_guidance_loss(dev))
             variants.update(variant_single_edits(dev, with_cpu=True))
+            variants.update(variant_set_foreground(dev))
         torch.cuda.empty_cache()
 
     line = None

@@ -247,7 +247,7 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
             }
         }
         for (int j = tid; j < mine; j += kPoissonThreads) o[list[k0 + j]] = (float)xs_[j];
-        if (gtid == 0 && iters_out) iters_out[e] = it;
+        if (gtid == 0 && iters_out) iters_out[e] = !(gam > stop) ? it : -it - 1;      // negative: stopped WITHOUT reaching the tolerance
         cluster.sync();          // no CTA exits while another may still read its shared memory
         return;
     }
@@ -330,7 +330,7 @@ __global__ void __cluster_dims__(kPoissonCluster, 1, 1) __launch_bounds__(kPoiss
         }
     }
     for (int k = gtid; k < n; k += gthreads) o[list[k]] = (float)x[k];
-    if (gtid == 0 && iters_out) iters_out[e] = it;
+    if (gtid == 0 && iters_out) iters_out[e] = !(gam > stop) ? it : -it - 1;      // negative: stopped WITHOUT reaching the tolerance
     cluster.sync();          // no CTA exits while another may still read its shared memory
 }
 

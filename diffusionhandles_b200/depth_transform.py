@@ -159,17 +159,34 @@ def _pack_mask(mask_f32: torch.Tensor) -> torch.Tensor:
     return bits
 
 
-def _poisson_device(image: torch.Tensor, mask_bits: torch.Tensor, lap_source: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _poisson_device(image: torch.Tensor, mask_bits: torch.Tensor, lap_source: Optional[torch.Tensor] = None,
+                    check: bool = False, what: str = "Poisson fill") -> torch.Tensor:
+    """fp64 CG fill on the device.  ``check=True`` reads the iteration counts back (one small synchronising copy) and warns
+    when a system stopped without reaching the tolerance - the reference's direct solver cannot fail that way."""
     lib = N.load()
     B, H, W = image.shape
     out = torch.empty_like(image)
     ws_bytes = int(lib.dh_poisson_workspace_bytes(B, H, W))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=image.device)
+    iters = torch.zeros(B, dtype=torch.int32, device=image.device)
     N.check(lib.dh_poisson_fill_source(N.ptr(image, torch.float32, "image"), N.ptr(mask_bits), None,
                                        N.ptr(lap_source, torch.float32, "lap_source") if lap_source is not None else None,
-                                       B, H, W, N.ptr(out), 0, 1e-13, None, N.ptr(ws), ws_bytes, N.stream_handle(image.device)),
+                                       B, H, W, N.ptr(out), 0, 1e-13, N.ptr(iters), N.ptr(ws), ws_bytes, N.stream_handle(image.device)),
             "dh_poisson_fill_source")
+    _poisson_device.last_iters = iters
+    if check:
+        warn_if_not_converged(iters, what)
     return out
+
+
+def warn_if_not_converged(iters: torch.Tensor, what: str) -> None:
+    """iters: the solver's per-system iteration counts (negative = stopped without reaching the tolerance)."""
+    it = iters.cpu().numpy()
+    bad = it < 0
+    if bad.any():
+        import warnings
+        warnings.warn(f"{what}: the conjugate-gradient solver did not reach its tolerance for {int(bad.sum())} of {len(it)} system(s) "
+                      f"(stopped after {int((-it[bad] - 1).max())} iterations); the filled values are approximate", RuntimeWarning)
 
 
 def poisson_solve(input_image, mask):
@@ -179,7 +196,7 @@ def poisson_solve(input_image, mask):
     arr = np.asarray(input_image)
     img = torch.as_tensor(arr, dtype=torch.float32, device=dev)[None].contiguous()
     m = torch.as_tensor(np.asarray(mask) != 0, device=dev).to(torch.float32)[None].contiguous()
-    out = _poisson_device(img, _pack_mask(m))
+    out = _poisson_device(img, _pack_mask(m), check=True, what="poisson_solve")
     return out[0].cpu().numpy().astype(arr.dtype)
 
 

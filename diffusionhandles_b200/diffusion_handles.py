@@ -72,7 +72,8 @@ class DiffusionHandles:
         rows = N.u32_array([((1 << (2 * (r - abs(i - r)) + 1)) - 1) << abs(i - r) for i in range(2 * r + 1)])
         dil = torch.empty_like(bits)
         N.check(lib.dh_morph_pass(N.ptr(bits), N.ptr(dil), 1, H, W, rows, 2 * r + 1, 2 * r + 1, 1, N.stream_handle(dev)), "dh_morph_pass")
-        return _poisson_device(d, dil, lap_source=b)[None]
+        # (the reference's set_foreground is synchronous CPU code: the convergence check's small read-back costs nothing extra)
+        return _poisson_device(d, dil, lap_source=b, check=True, what="set_foreground")[None]
 
     def edit_geometry(self, depth: torch.Tensor, fg_mask: torch.Tensor, bg_depth: torch.Tensor, rot_angle: float = None,
                       rot_axis: torch.Tensor = None, translation: torch.Tensor = None, use_input_depth_normalization=False):

@@ -151,7 +151,7 @@ class EditEngine:
         # relative residual at which the CG hole fill stops (fp64).  The filled disparity is cast to fp32: from 1e-9 downwards the
         # result does not change any more (tests/fuzz/poisson_tolerance.py), 1e-11 keeps two orders of margin for ill-conditioned holes
         self.poisson_rel_tol = 1e-11
-        self.n_pinned = torch.empty((2, B), dtype=i32).pin_memory()
+        self.n_pinned = torch.zeros((3, B), dtype=i32).pin_memory()
         # the transforms are uploaded from this (pageable, engine-owned) array: it outlives the call, so a CUDA graph that captured
         # the launch chain re-reads the transforms stored here at every replay
         self._rigids = (N.dh_rigid * B)()
@@ -222,9 +222,14 @@ class EditEngine:
         if sync_counts:
             self.n_pinned[0].copy_(self.n_corr, non_blocking=True)
             self.n_pinned[1].copy_(self.n_fg, non_blocking=True)
+            if poisson:
+                self.n_pinned[2].copy_(self.poisson_iters, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             res.n_corr_host = self.n_pinned[0].numpy().copy()
             res.n_fg_host = self.n_pinned[1].numpy().copy()
+            if poisson:
+                from .depth_transform import warn_if_not_converged
+                warn_if_not_converged(self.n_pinned[2], "hole fill of the edited disparity")
         return res
 
     def unpack_bits(self, bits: torch.Tensor) -> torch.Tensor:

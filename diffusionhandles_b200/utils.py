@@ -28,5 +28,5 @@ def solve_laplacian_depth(fg_depth, bg_depth, mask):
     img = torch.as_tensor(fg, dtype=torch.float32, device=dev)[None].contiguous()
     src = torch.as_tensor(np.asarray(bg_depth), dtype=torch.float32, device=dev)[None].contiguous()
     m = torch.as_tensor(np.asarray(mask) != 0, device=dev).to(torch.float32)[None].contiguous()
-    out = _poisson_device(img, _pack_mask(m), lap_source=src)
+    out = _poisson_device(img, _pack_mask(m), lap_source=src, check=True, what="solve_laplacian_depth")
     return out[0].cpu().numpy().astype(fg.dtype)

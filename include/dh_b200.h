@@ -294,7 +294,9 @@ int dh_scale_inplace_many(float* const* data_host, const size_t* n_host, int cou
 /* ---- 8(f) rank 1: Poisson hole fill of the edited disparity, depth_transform.py:346-363, :535-587 ----
  * Unknown pixels = mask_a XOR mask_b (cleaned ^ raw target mask; mask_b may be NULL).  Solves the masked
  * 5-point Laplace system (diag 4, known neighbours on the right-hand side) with fp64 conjugate gradients,
- * one CTA per edit; out = image with the unknown pixels replaced.  max_iter <= 0 -> 20000. */
+ * one 8-CTA cluster per edit; out = image with the unknown pixels replaced.  max_iter <= 0 -> 20000.
+ * iters_out (device int32[B], may be NULL): iterations taken; NEGATIVE (-iterations - 1) when the solver stopped without
+ * reaching rel_tol (iteration cap or breakdown) - the caller decides whether to warn or raise. */
 size_t dh_poisson_workspace_bytes(int B, int H, int W);
 int dh_poisson_fill(const float* image, const uint32_t* mask_a_bits, const uint32_t* mask_b_bits, int B, int H, int W,
                     float* out, int max_iter, double rel_tol, int32_t* iters_out, void* ws, size_t ws_bytes, void* stream);

@@ -1110,3 +1110,122 @@ def test_edit_fast_splat_equals_all_points_formulation(dev, K, H, W):
             assert torch.equal(a, b), k
     for a, b in zip(out[(True, True)]["points"], ref["points"]):
         assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+
+
+def test_poisson_large_hole_and_non_convergence_flag(dev):
+    """A 220 x 220 hole (48,400 unknowns: beyond the shared-memory solver, the global-memory path) against SuperLU, and the
+    convergence report: iters_out is negative when the iteration cap stops the solver before the tolerance is reached."""
+    import warnings
+    from diffusionhandles_b200 import depth_transform as dt
+    from diffusionhandles_b200 import _native as Nn
+    S = 512
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float32)
+    img = (100.0 + 40.0 * np.sin(xx / 37.0) * np.cos(yy / 53.0) + 0.1 * yy).astype(np.float32)
+    mask = np.zeros((S, S), np.uint8)
+    mask[140:360, 150:370] = 1
+    ref = O.poisson_solve(img, mask)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                      # a converged solve must not warn
+        got = dt.poisson_solve(img, mask)
+    assert np.abs(got - ref).max() <= 1e-4 * float(img.max() - img.min())
+    assert int(dt._poisson_device.last_iters[0]) > 0
+    # the cap: three iterations cannot reach 1e-13
+    lib = Nn.load()
+    t_img = torch.from_numpy(img).to(dev)[None].contiguous()
+    bits = dt._pack_mask(torch.from_numpy(mask.astype(np.float32)).to(dev)[None].contiguous())
+    out = torch.empty_like(t_img)
+    ws = torch.empty(int(lib.dh_poisson_workspace_bytes(1, S, S)), dtype=torch.uint8, device=dev)
+    iters = torch.zeros(1, dtype=torch.int32, device=dev)
+    Nn.check(lib.dh_poisson_fill(Nn.ptr(t_img), Nn.ptr(bits), None, 1, S, S, Nn.ptr(out), 3, 1e-13, Nn.ptr(iters), Nn.ptr(ws), ws.numel(),
+                                 Nn.stream_handle(dev)), "dh_poisson_fill")
+    assert int(iters[0]) == -4
+    with pytest.warns(RuntimeWarning):
+        dt.warn_if_not_converged(iters, "test")
+
+
+def test_guided_inference_reference_signature_with_injected_models(dev, K, golden_pc):
+    """GuidedStableDiffuser.guided_inference (guided_stable_diffuser.py:291-488) with a small stand-in U-Net / scheduler injected:
+    the loop (schedule, fused K4 loss, latents -= 0.1 grad, CFG 7.5, scheduler step) against the same loop written with plain
+    torch index gathers (losses.py:4-84) and autograd."""
+    from types import SimpleNamespace
+    import torch.nn.functional as F
+    from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser, make_guidance_weight_schedule
+    meta, g = golden_pc
+    corr = torch.from_numpy(g["cfg1/corr"].astype(np.int64))
+    torch.manual_seed(0)
+
+    class TinyUNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(sample_size=64)
+            self.c0 = torch.nn.Conv2d(5, 6, 3, padding=1, stride=2)
+            self.c1 = torch.nn.Conv2d(5, 5, 3, padding=1)
+            self.c2 = torch.nn.Conv2d(5, 4, 3, padding=1)
+            self.out = torch.nn.Conv2d(5, 4, 3, padding=1)
+
+        def forward(self, x, t, encoder_hidden_states=None, cross_attention_kwargs=None, return_dict=False):
+            s = float(t) / 1000.0 + encoder_hidden_states.mean()
+            return (self.out(x) * 0.1, None, None, None, torch.tanh(self.c0(x) + s), torch.tanh(self.c1(x) - s), torch.tanh(self.c2(x) * 2 + s))
+
+    class TinyScheduler:
+        order = 1
+
+        def set_timesteps(self, n, device=None):
+            self.timesteps = torch.linspace(900, 100, n, device=device)
+
+        def scale_model_input(self, x, t):
+            return x * 0.9
+
+        def step(self, noise, t, latents, eta=0.0, return_dict=False):
+            return (latents - 0.05 * noise,)
+
+    conf = SimpleNamespace(fg_weight=1.5, bg_weight=1.25, fg_patch_size=1, bg_patch_size=1, use_depth=True, bg_loss_type='global_avg',
+                           num_timesteps=3, num_optsteps=2, guidance_max_step=2, guidance_schedule_type='constant', bg_erosion=0, seed=7)
+    unet = TinyUNet().to(dev)
+    for p_ in unet.parameters():
+        p_.requires_grad_(False)
+    gsd = GuidedStableDiffuser(conf, unet=unet, scheduler=TinyScheduler()).to(dev)
+    T = conf.num_timesteps
+    gen = torch.Generator(device=dev).manual_seed(3)
+    latents0 = torch.randn((1, 4, 64, 64), generator=gen, device=dev)
+    depth = torch.rand((1, 1, 512, 512), generator=gen, device=dev) + 1.0
+    cond = torch.randn((1, 7, 8), generator=gen, device=dev) * 0.1
+    uncond = torch.randn((T, 1, 7, 8), generator=gen, device=dev) * 0.1
+    acts_orig = [torch.randn((T, c, s, s), generator=gen, device=dev) for c, s in ((6, 32), (5, 64), (4, 64))]
+    out = gsd.guided_inference(latents0.clone(), depth, uncond, cond, acts_orig, corr)
+    assert out.shape == (1, 4, 64, 64)                       # (no VAE injected: the final latents are returned)
+
+    # ---- the same loop with torch gathers ----
+    pc = O.process_correspondences(corr.numpy(), 512, 0)
+    ix = {k: torch.from_numpy(v).to(dev) for k, v in pc.items()}
+    sched = make_guidance_weight_schedule(1.5, 1.25, 2, 'constant')
+    d64 = gsd.init_depth(depth)
+    tsch = TinyScheduler(); tsch.set_timesteps(T, device=dev)
+    lat = latents0.clone()
+
+    def up(a):
+        return a if a.shape[-1] == 64 else F.interpolate(a[None], size=(64, 64), mode="bilinear", align_corners=False)[0]
+    for t_idx, t in enumerate(tsch.timesteps):
+        it = 0
+        while it < 2 and t_idx < 2:
+            l_ = lat.detach().requires_grad_(True)
+            o_ = unet(torch.cat([tsch.scale_model_input(l_, t), d64], dim=1), t, encoder_hidden_states=cond)
+            fgw, bgw = sched(t_idx, it)
+            loss = 0.0
+            for li, a in enumerate((o_[4], o_[5], o_[6])):
+                cur, org = up(a[0]), up(acts_orig[li][t_idx])
+                fg = (org[:, ix["original_y"], ix["original_x"]] - cur[:, ix["transformed_y"], ix["transformed_x"]]).abs().mean(-1).mean()
+                bg = (org[:, ix["background_y_orig"], ix["background_x_orig"]].mean(-1) -
+                      cur[:, ix["background_y_trans"], ix["background_x_trans"]].mean(-1)).abs().mean()
+                loss = loss + fgw[li] * fg + bgw[li] * bg
+            lat = l_.detach() - 0.1 * torch.autograd.grad(loss, [l_])[0]
+            it += 1
+        with torch.no_grad():
+            x2 = torch.cat([tsch.scale_model_input(torch.cat([lat] * 2), t), torch.cat([d64] * 2, dim=0)], dim=1)
+            emb = torch.cat([uncond[t_idx].expand(*cond.shape), cond])
+            n = unet(x2, t, encoder_hidden_states=emb)[0]
+            nu, nt = n.chunk(2)
+            lat = tsch.step(nu + 7.5 * (nt - nu), t, lat)[0]
+    assert torch.allclose(out, lat, rtol=1e-4, atol=1e-5), float((out - lat).abs().max())
+    with pytest.raises(NotImplementedError):
+        GuidedStableDiffuser(conf).guided_inference(latents0, depth, uncond, cond, acts_orig, corr)
