@@ -11,7 +11,7 @@ from typing import Callable, List, Optional, Sequence
 import torch
 
 from .guided_stable_diffuser import make_guidance_weight_schedule
-from .losses import guidance_loss
+from .losses import guidance_loss, guidance_loss_and_grad
 
 
 def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, scheduler_step: Callable,
@@ -43,7 +43,14 @@ def guided_denoise(latents: torch.Tensor, timesteps: Sequence, unet: Callable, s
                     keep = [i for i in range(len(acts)) if fgw[i] != 0.0 or bgw[i] != 0.0]
                     acts, origs = [acts[i] for i in keep], [origs[i] for i in keep]
                     fgw, bgw = [fgw[i] for i in keep], [bgw[i] for i in keep]
-                if acts:
+                if acts and (bg_loss_type != 'local_avg' or bg_patch_size == fg_patch_size):
+                    # value and d(loss)/d(activations) from one fused launch; the U-Net's backward then carries them to the latents
+                    # (the chain rule of autograd.grad(loss, latents), guided_stable_diffuser.py:430-434)
+                    _, _, act_grads = guidance_loss_and_grad(acts, origs, processed_correspondences, fgw, bgw, bg_loss_type=bg_loss_type,
+                                                             activations_size=activations_size, patch_size=fg_patch_size)
+                    grad = torch.autograd.grad(acts, [lat], grad_outputs=act_grads)[0]
+                    latents = lat.detach() - grad * step_size
+                elif acts:
                     loss, _ = guidance_loss(acts, origs, processed_correspondences, fgw, bgw, bg_loss_type=bg_loss_type,
                                             activations_size=activations_size, patch_size=fg_patch_size,
                                             bg_patch_size=bg_patch_size)

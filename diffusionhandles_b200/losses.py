@@ -29,6 +29,12 @@ def _to_cells(y, x, grid: int, device) -> torch.Tensor:
                 raise IndexError(f"{name} index out of range for a {grid} x {grid} loss grid: [{a.min()}, {a.max()}]")
     yy = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y).to(device=device, dtype=torch.int64)
     xx = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(device=device, dtype=torch.int64)
+    dev_checked = [(n, v) for n, v in (("y", y), ("x", x)) if isinstance(v, torch.Tensor) and v.is_cuda and v.numel()]
+    if dev_checked:      # index tensors that live on the device: one small read-back (these entry points build a plan, which syncs anyway)
+        ext = torch.stack([torch.stack([v.min(), v.max()]) for _, v in dev_checked]).cpu()
+        for (n, _), (lo, hi) in zip(dev_checked, ext.tolist()):
+            if lo < 0 or hi >= grid:
+                raise IndexError(f"{n} index out of range for a {grid} x {grid} loss grid: [{int(lo)}, {int(hi)}]")
     return (yy.reshape(-1) * grid + xx.reshape(-1)).to(torch.int32).contiguous()
 
 
@@ -54,6 +60,13 @@ class LossPlan:
         self.grid = grid
         self.n = [int(t.numel()) if t is not None else 0 for t in (fg_src, bg_orig, bg_trans, bg_common)]
         n_fg = self.n[0]
+        # the kernels index shared / global memory with these cell ids: range-check them on the device (the reference's tensor
+        # indexing raises IndexError); the single read-back rides on the synchronisation the header read below needs anyway
+        lists = [t for t in (fg_src, fg_dst, bg_orig, bg_trans, bg_common) if t is not None and t.numel()]
+        if lists:
+            ext = torch.stack([torch.stack([t.min(), t.max()]) for t in lists]).cpu()
+            if int(ext[:, 0].min()) < 0 or int(ext[:, 1].max()) >= grid * grid:
+                raise IndexError(f"index out of range for a {grid} x {grid} loss grid (cell ids span [{int(ext[:, 0].min())}, {int(ext[:, 1].max())}])")
         plan_bytes = int(lib.dh_loss_plan_bytes(grid, n_fg))
         ws_bytes = int(lib.dh_loss_plan_workspace_bytes(grid, n_fg))
         if plan_bytes == 0:
@@ -102,10 +115,9 @@ def _plan_for(pc, grid: int, device, keys=("fg_src", "fg_dst", "bg_orig", "bg_tr
 
 
 def _as_f32(t: torch.Tensor, dev) -> torch.Tensor:
-    t = t.detach()
     if t.dtype is torch.float32 and t.device == dev and t.is_contiguous():
-        return t
-    return t.to(device=dev, dtype=torch.float32).contiguous()
+        return t            # (only its data pointer is used: no detach needed)
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
 def _launch(curs: Sequence[torch.Tensor], origs: Sequence[torch.Tensor], want_grad: Sequence[bool],
@@ -182,9 +194,13 @@ class _FusedLoss(torch.autograd.Function):
         return total, parts
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_total, _g_parts):
         lib = N.load()
         res = [None] * (1 + ctx.n_inputs)
+        if ctx.grads is None:       # the gradient was produced by the forward pass and handed out (scaled in place) by the first backward
+            raise RuntimeError("Trying to backward through the fused guidance loss a second time: its gradient buffers have already been "
+                               "handed out. Re-evaluate the loss instead (retain_graph is not supported for this node).")
         live = [(i, g) for i, g in enumerate(ctx.grads) if g is not None]
         ctx.grads = None
         if live:
@@ -244,6 +260,23 @@ def guidance_loss(activations: Sequence[torch.Tensor], activations_orig: Sequenc
     bg_total, bg_parts = _FusedLoss.apply(dict(L=L, fgw=zeros, bgw=list(bg_weights), plan=plan, fg_kind=0, bg_kind=bg_kind, patch=bg_patch),
                                           *activations, *activations_orig)
     return fg_total + bg_total, fg_parts + bg_parts
+
+
+def guidance_loss_and_grad(activations: Sequence[torch.Tensor], activations_orig: Sequence[torch.Tensor], processed_correspondences,
+                           fg_weights: Sequence[float], bg_weights: Sequence[float], bg_loss_type: str = 'global_avg',
+                           activations_size=(64, 64), patch_size: int = 1):
+    """The same value as ``guidance_loss`` together with d(total)/d(activations[l]) for every layer, WITHOUT going through
+    autograd: one fused launch, no graph node, no backward pass.  ``guided_denoise`` uses it and feeds the gradients to the
+    U-Net's backward as ``grad_outputs`` (the chain rule the reference's ``autograd.grad(loss, latents)`` applies,
+    guided_stable_diffuser.py:430-434).  Returns (total 0-d tensor, per-term values (2L,), [grad_l (C_l,h_l,w_l)])."""
+    if bg_loss_type not in ('global_avg', 'local_avg'):
+        raise ValueError(f'Unknown background loss type: {bg_loss_type}')
+    grid = _grid_of(activations_size)
+    plan = _plan_for(processed_correspondences, grid, activations[0].device)
+    L = len(activations)
+    out, grads = _launch(activations, activations_orig, [True] * L, fg_weights, bg_weights, plan, _FG,
+                         _BG_GLOBAL if bg_loss_type == 'global_avg' else _BG_LOCAL, _patch_of(patch_size))
+    return out[0], out[1:], grads
 
 
 def compute_foreground_loss(activations, activations_orig, processed_correspondences, patch_size, activations_size):

@@ -1008,6 +1008,17 @@ def test_loss_index_lists_are_range_checked(dev):
     with pytest.raises(IndexError):
         losses.average_feat_l1_loss(f1, f2, ok, ok, ok, np.array([-1, 2, 3]))
     assert torch.isfinite(losses.local_average_feat_l1_loss(f1, f2, ok, ok, ok, ok))
+    # index tensors that already live on the device are checked too (the kernels index shared memory with them)
+    okd = torch.tensor([1, 2, 3], device=dev)
+    with pytest.raises(IndexError):
+        losses.local_average_feat_l1_loss(f1, f2, torch.tensor([1, 64, 3], device=dev), okd, okd, okd)
+    with pytest.raises(IndexError):
+        losses.average_feat_l1_loss(f1, f2, okd, okd, okd, torch.tensor([-1, 2, 3], device=dev))
+    # a second backward through the same graph raises (the gradient was produced by the forward pass and handed out once)
+    loss = losses.local_average_feat_l1_loss(f1, f2, okd, okd, okd, okd)
+    torch.autograd.grad(loss, f2, retain_graph=True)
+    with pytest.raises(RuntimeError):
+        torch.autograd.grad(loss, f2)
 
 
 def test_poisson_solve_large_system_uses_the_global_path(dev):
