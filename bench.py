@@ -638,7 +638,7 @@ def run_ours(args):
 
     # ---- end to end through the public batched API with pinned HOST buffers ----
     e2e_steps = max(2, min(args.steps, 5))
-    pipe = EditWarpPipeline(dev, S, LEVELS, chunk=16, n_streams=3, full_winner_map=True)
+    pipe = EditWarpPipeline(dev, S, LEVELS, chunk=16, n_streams=4, full_winner_map=True)      # (tools/tune_e2e.py sweep)
     levels_h = [torch.empty((n_edits, c, s, s), dtype=torch.float32).pin_memory() for c, s in LEVELS]
     for h, d in zip(levels_h, levels):
         h.copy_(d)

@@ -52,10 +52,11 @@ wl = build_workload(dev, n, full_map=True)
 levels_h = [torch.randn((n, c, s, s), dtype=torch.float32).pin_memory() for c, s in LEVELS]
 outs_h = [torch.empty((n, c, s, s), dtype=torch.float32).pin_memory() for c, s in LEVELS]
 n_corr_h = torch.empty(n, dtype=torch.int32).pin_memory()
-for chunk, streams in [(16, 3), (8, 3), (8, 4), (16, 2), (16, 4), (32, 2), (32, 3), (4, 4), (64, 2)]:
+for chunk, streams in [(16, 3), (8, 3), (8, 4), (16, 4), (4, 4), (4, 6), (8, 6), (32, 3)]:
     pipe = EditWarpPipeline(dev, S, LEVELS, chunk=chunk, n_streams=streams, full_winner_map=True)
-    t = timed(lambda: pipe.run_host(wl["depth_h"], wl["bg_h"], wl["mask_h"], wl["K"], wl["rigids"], levels_h, outs_h, n_corr_h))
-    bytes_in, bytes_out = pipe.h2d_bytes_per_edit() * n, pipe.d2h_bytes_per_edit() * n
+    t = timed(lambda: pipe.run_host(wl["scene_h"][0], wl["scene_h"][1], wl["scene_h"][2], wl["K"], wl["rigids"], levels_h, outs_h, n_corr_h,
+                                    scene_index=wl["scene_index"]))
+    bytes_in, bytes_out = pipe.h2d_bytes_per_edit(edits_per_scene=16) * n, pipe.d2h_bytes_per_edit() * n
     print(json.dumps({"chunk": chunk, "streams": streams, "warps_per_s": n / t, "h2d_GBs": bytes_in / t / 1e9,
                       "d2h_GBs": bytes_out / t / 1e9}), flush=True)
     del pipe
