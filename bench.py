@@ -456,7 +456,10 @@ def variant_strong_scaling(dev, rank, world, steps=5):
     levels = [torch.randn((len(mine), c, s, s), generator=gen, dtype=torch.float32, device=dev) for c, s in LEVELS]
     n_local = len(mine)
     chunk = n_local if n_local <= 64 else 64
-    sweep = DeviceSweep(dev, S, LEVELS, depth, bg, mask, K, rigids, levels, chunk=chunk, use_graph=True)
+    # small shards are latency bound (the exact sequential centroid alone is ~0.17 ms): their chain is captured as parallel
+    # sub-chains (tools/sweep_branches.py)
+    branches = int(os.environ.get("DH_BENCH_BRANCHES", "8" if n_local <= 32 and n_local % 8 == 0 else "1"))
+    sweep = DeviceSweep(dev, S, LEVELS, depth, bg, mask, K, rigids, levels, chunk=chunk, use_graph=True, branches=branches)
     sweep.capture()
     # the replayed graphs must give what the plain launch chain gives (first chunk: counts and the warped stack)
     sweep.run()
@@ -489,7 +492,7 @@ def variant_strong_scaling(dev, rank, world, steps=5):
     ms = float(t.item())
     n_corr_sum = int(out[:, 0].sum().item()) if rank == 0 else None
     del sweep
-    return {"config4_strong": {"edits_total": total, "edits_per_rank": n_local, "chunk": chunk, "ms_per_sweep": ms,
+    return {"config4_strong": {"edits_total": total, "edits_per_rank": n_local, "chunk": chunk, "graph_branches": branches, "ms_per_sweep": ms,
                                "edits_per_s": total / ms * 1e3, "n_corr_sum": n_corr_sum,
                                "what": "K1,K2,masks,correspondences,dense maps,K3 per edit (device-resident, CUDA-graph replay per chunk) + "
                                        "one NCCL gather of the result records; device time, max over ranks",
@@ -564,6 +567,14 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _native.load()
+    if os.environ.get("DH_BENCH_ONLY_STRONG"):          # developer shortcut: only the strong-scaling variant
+        v = variant_strong_scaling(dev, rank, world)
+        if rank == 0:
+            print(json.dumps(v), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # host threads + pinned staging buffers on the GPU's own NUMA node (matters for the e2e leg at N > 1)
     full_affinity = os.sched_getaffinity(0)
     host_binding = bind_host_to_gpu_numa_node(dev) if os.environ.get("DH_BENCH_NUMA_BIND", "1") == "1" else None

@@ -148,39 +148,65 @@ class DeviceSweep:
 
     def __init__(self, device: torch.device, S: int, level_shapes: Sequence[Tuple[int, int]], depth: torch.Tensor, bg: torch.Tensor,
                  mask: torch.Tensor, intrinsics: torch.Tensor, rigids: Sequence[N.dh_rigid], levels: Sequence[torch.Tensor],
-                 chunk: Optional[int] = None, use_graph: bool = True, full_winner_map: bool = True):
+                 chunk: Optional[int] = None, use_graph: bool = True, full_winner_map: bool = True, branches: int = 1):
+        """``branches`` > 1 (graphs only): a chunk is cut into that many sub-chunks whose launch chains are captured on forked
+        streams, i.e. as parallel branches of the graph.  At small chunks every kernel of the chain is latency bound (the exact
+        sequential centroid alone is ~0.17 ms whatever the batch), so independent sub-chains overlap almost perfectly."""
         self.device = torch.device(device)
         E = depth.shape[0]
         self.E, self.S = E, S
         self.chunk = chunk or E
         if E % self.chunk:
             raise ValueError(f"number of edits {E} must be a multiple of the chunk size {self.chunk}")
+        self.branches = branches if use_graph else 1
+        if self.chunk % self.branches:
+            raise ValueError(f"chunk size {self.chunk} must be a multiple of the number of branches {self.branches}")
+        self.sub = self.chunk // self.branches
         self.sides = [s for _, s in level_shapes]
         self.depth, self.bg, self.mask, self.K, self.rigids, self.levels = depth, bg, mask, intrinsics, list(rigids), list(levels)
         self.outs = [torch.empty_like(l) for l in levels]
         self.n_corr = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.rec = torch.zeros((E, 2), dtype=torch.int64, device=self.device)     # per-edit result records (filled inside the chain)
         self.full_winner_map = full_winner_map
-        # one engine (scratch) per chunk position when graphs are used: a captured chain is bound to its buffers
+        # one engine (scratch) per sub-chunk position when graphs are used: a captured chain is bound to its buffers
         n_chunks = E // self.chunk
-        self.engines = [EditEngine(self.device, self.chunk, S, S) for _ in range(n_chunks if use_graph else 1)]
+        self.engines = [EditEngine(self.device, self.sub, S, S) for _ in range(n_chunks * self.branches if use_graph else 1)]
         self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * n_chunks
         self.use_graph = use_graph
-        self.launches_per_chunk = 25
+        self.launches_per_chunk = 25 * self.branches
 
-    def _chunk(self, ci: int):
-        e0, e1 = ci * self.chunk, (ci + 1) * self.chunk
-        eng = self.engines[ci if self.use_graph else 0]
+    def _part(self, ci: int, bi: int):
+        e0 = ci * self.chunk + bi * self.sub
+        e1 = e0 + self.sub
+        eng = self.engines[ci * self.branches + bi if self.use_graph else 0]
         res = eng.run(self.depth[e0:e1], self.bg[e0:e1], self.mask[e0:e1], self.K, self.rigids[e0:e1], poisson=False,
                       sync_counts=False)
         maps = warp.dense_source_maps(res.corr, res.n_corr, self.S, self.sides, res.winner_src if self.full_winner_map else None)
         warp.warp_stacks([l[e0:e1] for l in self.levels], maps, [o[e0:e1] for o in self.outs])
         self.n_corr[e0:e1].copy_(res.n_corr)
+        # fixed-size result record of every edit: (n_corr, 64-bit checksum of the smallest warped level) - part of the captured chain
+        self.rec[e0:e1, 0].copy_(res.n_corr)
+        torch.sum(self.outs[-1][e0:e1].flatten(1).view(torch.int32), 1, dtype=torch.int64, out=self.rec[e0:e1, 1])
+
+    def _chunk(self, ci: int, forks=None):
+        if forks is None or self.branches == 1:
+            for bi in range(self.branches):
+                self._part(ci, bi)
+            return
+        main = torch.cuda.current_stream(self.device)
+        for bi, st in enumerate(forks):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self._part(ci, bi)
+        for st in forks:
+            main.wait_stream(st)
 
     def capture(self):
         """Warm up every chunk once, then capture it (idempotent)."""
         if not self.use_graph or all(g is not None for g in self.graphs):
             return
         side = torch.cuda.Stream(device=self.device)
+        forks = [torch.cuda.Stream(device=self.device) for _ in range(self.branches)] if self.branches > 1 else None
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for ci in range(len(self.graphs)):
@@ -189,7 +215,7 @@ class DeviceSweep:
             for ci in range(len(self.graphs)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    self._chunk(ci)
+                    self._chunk(ci, forks)
                 self.graphs[ci] = g
         torch.cuda.current_stream(self.device).wait_stream(side)
 
@@ -205,8 +231,7 @@ class DeviceSweep:
 
     def records(self) -> torch.Tensor:
         """Fixed-size per-edit result records (n_corr, 64-bit checksum of the first warped level) for the result gather."""
-        chk = self.outs[-1].flatten(1).view(torch.int32).sum(1, dtype=torch.int64)      # (the smallest level: cheap)
-        return torch.stack([self.n_corr.to(torch.int64), chk], dim=1).contiguous()
+        return self.rec
 
 
 def gather_records(records: torch.Tensor, dst: int = 0):
@@ -215,12 +240,9 @@ def gather_records(records: torch.Tensor, dst: int = 0):
     Works with any torch.distributed backend (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
-    buf = [torch.empty_like(records) for _ in range(world)] if rank == dst else None
-    dist.gather(records, buf, dst=dst)
+    buf = torch.empty((world,) + tuple(records.shape), dtype=records.dtype, device=records.device) if rank == dst else None
+    dist.gather(records, list(buf.unbind(0)) if rank == dst else None, dst=dst)
     if rank != dst:
         return None
-    n_local = records.shape[0]
-    out = torch.empty((n_local * world,) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
-    for r in range(world):
-        out[r::world] = buf[r]
-    return out
+    # (world, n_local, k) -> (n_local, world, k) -> (n_local * world, k): row e = edit e, one copy
+    return buf.transpose(0, 1).reshape((records.shape[0] * world,) + tuple(records.shape[1:]))
