@@ -4,7 +4,9 @@
 scene of meshes by z-buffer splatting their VERTICES with K2 (bit-exact (z, index) tie-break, meshes earlier in
 the list win ties - like ``join_meshes_as_scene([bg, fg])``) and exposes the two layers the path uses
 (depth_transform.py:152): ``world_position`` and ``flat_vertex_color`` as (B,H,W,4) tensors, alpha in channel 3.
-It is NOT a triangle rasteriser: the mesh mode's pytorch3d semantics are unpinned.
+``MeshRenderer`` (= ``PyTorch3DRenderer``) is the hard z-buffer TRIANGLE rasteriser of mesh mode (``dh_raster.cu``), written to
+pytorch3d's published ``rasterize_meshes`` semantics; pytorch3d itself is not available here, so that parity is unpinned
+(SURVEY.md 8(c), 8(f) rank 2).
 """
 from __future__ import annotations
 
