@@ -14,8 +14,8 @@ namespace dh {
 
 thread_local int g_last_cuda_error = 0;
 
-constexpr int kTile = 4096;          // pixels per compaction tile
-constexpr int kTileThreads = 1024;   // 4 pixels per thread
+constexpr int kTile = 1024;          // pixels per compaction tile (small tiles: the block scans are latency bound, eight blocks per SM)
+constexpr int kTileThreads = 256;    // 4 pixels per thread
 
 struct CamDev {
     float k[9];
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTileThreads) fg_count_kernel(const float* __r
     if (lane_id() == 0) warp_sums[warp_id()] = c;
     __syncthreads();
     if (warp_id() == 0) {
-        int s = warp_sums[lane_id()];
+        int s = lane_id() < (int)(blockDim.x >> 5) ? warp_sums[lane_id()] : 0;
         s = __reduce_add_sync(0xFFFFFFFFu, s);
         if (lane_id() == 0) tile_counts[e * ntiles + tile] = s;
     }
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kTileThreads) edit_prepare_kernel(
     if (lane_id() == 0) warp_sums[warp_id()] = c;
     __syncthreads();
     if (warp_id() == 0) {
-        int s = warp_sums[lane_id()];
+        int s = lane_id() < (int)(blockDim.x >> 5) ? warp_sums[lane_id()] : 0;
         s = __reduce_add_sync(0xFFFFFFFFu, s);
         if (lane_id() == 0) tile_counts[e * ntiles + tile] = s;
     }

@@ -12,6 +12,11 @@ namespace dh {
 struct Element {
     uint32_t rows[32];
     int k_rows, k_cols;
+    // rows with the same bit pattern form a group: shifts distribute over OR / AND, so the source rows of a group are combined
+    // first and the horizontal taps are applied ONCE per group (the 10 x 10 ellipse: 4 patterns, 27 taps instead of 83)
+    int n_groups;
+    uint32_t group_pattern[32];
+    uint32_t group_rows[32];      // bit i: element row i belongs to the group
 };
 
 __global__ void __launch_bounds__(256) morph_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
@@ -26,21 +31,26 @@ __global__ void __launch_bounds__(256) morph_kernel(const uint32_t* __restrict__
     const int tail = W - (wpr - 1) * 32;                   // valid bits in the last word of a row
     const uint32_t tail_mask = tail >= 32 ? 0xFFFFFFFFu : ((1u << tail) - 1u);
     uint32_t acc = fill;
-    for (int i = 0; i < el.k_rows; ++i) {
-        const uint32_t er = el.rows[i];
-        const int rr = row + i - ay;
-        if (er == 0 || rr < 0 || rr >= H) continue;
-        const uint32_t* r = s + (size_t)rr * wpr;
-        uint32_t left = wc > 0 ? r[wc - 1] : fill;
-        uint32_t mid = r[wc];
-        uint32_t right = wc + 1 < wpr ? r[wc + 1] : fill;
-        if (!dilate) {   // padding bits beyond W are stored as 0 but must not constrain an erosion
-            if (wc == wpr - 1) mid |= ~tail_mask;
-            if (wc + 1 == wpr - 1) right |= ~tail_mask;
+    for (int g = 0; g < el.n_groups; ++g) {
+        uint32_t left = fill, mid = fill, right = fill;
+        bool any = false;
+        for (uint32_t rows = el.group_rows[g]; rows; rows &= rows - 1) {
+            const int rr = row + (__ffs(rows) - 1) - ay;
+            if (rr < 0 || rr >= H) continue;                 // rows outside the image do not contribute
+            const uint32_t* r = s + (size_t)rr * wpr;
+            uint32_t l = wc > 0 ? r[wc - 1] : fill;
+            uint32_t m = r[wc];
+            uint32_t rt = wc + 1 < wpr ? r[wc + 1] : fill;
+            if (!dilate) {   // padding bits beyond W are stored as 0 but must not constrain an erosion
+                if (wc == wpr - 1) m |= ~tail_mask;
+                if (wc + 1 == wpr - 1) rt |= ~tail_mask;
+            }
+            if (dilate) { left |= l; mid |= m; right |= rt; } else { left &= l; mid &= m; right &= rt; }
+            any = true;
         }
-        for (int j = 0; j < el.k_cols; ++j) {
-            if (!((er >> j) & 1u)) continue;
-            const int dx = j - ax;
+        if (!any) continue;
+        for (uint32_t pat = el.group_pattern[g]; pat; pat &= pat - 1) {
+            const int dx = (__ffs(pat) - 1) - ax;
             uint32_t w;
             if (dx == 0) w = mid;
             else if (dx > 0) w = __funnelshift_r(mid, right, dx);
@@ -72,7 +82,8 @@ __global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t* __rest
 // ------------------------------------------------------------------------------------------------
 // correspondences: ordered compaction of the visible foreground points that survive the cleaned mask
 // ------------------------------------------------------------------------------------------------
-constexpr int kCorrTile = 4096;
+constexpr int kCorrTile = 1024;      // foreground points per tile (small tiles: the block scans are latency bound)
+constexpr int kCorrThreads = kCorrTile / 4;
 
 __device__ __forceinline__ bool corr_keep(const int32_t* pix, const uint32_t* winner, const uint32_t* cleaned,
                                           int e, int j, int P, int W, int wpr, int H, int stride, int& q) {
@@ -83,12 +94,16 @@ __device__ __forceinline__ bool corr_keep(const int32_t* pix, const uint32_t* wi
     return (cleaned[(size_t)e * H * wpr + row * wpr + (col >> 5)] >> (col & 31)) & 1u;
 }
 
-__global__ void __launch_bounds__(1024) corr_count_kernel(const int32_t* __restrict__ pix, const uint32_t* __restrict__ winner,
+__global__ void __launch_bounds__(kCorrThreads) corr_count_kernel(const int32_t* __restrict__ pix, const uint32_t* __restrict__ winner,
                                                           const int32_t* __restrict__ n_fg, const uint32_t* __restrict__ cleaned,
                                                           int H, int W, int wpr, int stride, int ntiles, int32_t* __restrict__ tile_counts) {
     __shared__ int warp_sums[32];
     const int e = blockIdx.y, tile = blockIdx.x, P = H * W;
     const int n = n_fg[e];
+    if (tile * kCorrTile >= n) {          // (the grid covers P points, an edit has n_fg << P)
+        if (threadIdx.x == 0) tile_counts[e * ntiles + tile] = 0;
+        return;
+    }
     int c = 0;
     const int j0 = tile * kCorrTile + threadIdx.x * 4;
 #pragma unroll
@@ -100,12 +115,12 @@ __global__ void __launch_bounds__(1024) corr_count_kernel(const int32_t* __restr
     if (lane_id() == 0) warp_sums[warp_id()] = c;
     __syncthreads();
     if (warp_id() == 0) {
-        int s = __reduce_add_sync(0xFFFFFFFFu, warp_sums[lane_id()]);
+        int s = __reduce_add_sync(0xFFFFFFFFu, lane_id() < (int)(blockDim.x >> 5) ? warp_sums[lane_id()] : 0);
         if (lane_id() == 0) tile_counts[e * ntiles + tile] = s;
     }
 }
 
-__global__ void __launch_bounds__(1024) corr_emit_kernel(const int32_t* __restrict__ pix, const uint32_t* __restrict__ winner,
+__global__ void __launch_bounds__(kCorrThreads) corr_emit_kernel(const int32_t* __restrict__ pix, const uint32_t* __restrict__ winner,
                                                          const int32_t* __restrict__ fg_index, const int32_t* __restrict__ n_fg,
                                                          const uint32_t* __restrict__ cleaned, int H, int W, int wpr, int stride,
                                                          int ntiles, const int32_t* __restrict__ tile_counts,
@@ -114,8 +129,10 @@ __global__ void __launch_bounds__(1024) corr_emit_kernel(const int32_t* __restri
     __shared__ int base_smem;
     const int e = blockIdx.y, tile = blockIdx.x, P = H * W;
     const int n = n_fg[e];
+    if (tile * kCorrTile >= n && tile != ntiles - 1) return;      // nothing to emit (the last tile still publishes the count)
     int part = 0;
-    for (int t = threadIdx.x; t < tile; t += blockDim.x) part += tile_counts[e * ntiles + t];
+    const int t_end = min(tile, (n + kCorrTile - 1) / kCorrTile);  // tiles beyond the edit's points hold zeros
+    for (int t = threadIdx.x; t < t_end; t += blockDim.x) part += tile_counts[e * ntiles + t];
     int tot;
     block_exclusive_scan(part, scan_smem, tot);
     if (threadIdx.x == 0) base_smem = tot;
@@ -350,6 +367,16 @@ static int make_element(const uint32_t* rows_host, int k_rows, int k_cols, Eleme
     for (int i = 0; i < 32; ++i) el->rows[i] = i < k_rows ? rows_host[i] : 0u;
     el->k_rows = k_rows;
     el->k_cols = k_cols;
+    el->n_groups = 0;
+    for (int i = 0; i < 32; ++i) { el->group_pattern[i] = 0u; el->group_rows[i] = 0u; }
+    for (int i = 0; i < k_rows; ++i) {
+        const uint32_t pat = k_cols >= 32 ? el->rows[i] : (el->rows[i] & ((1u << k_cols) - 1u));
+        if (!pat) continue;
+        int g = 0;
+        while (g < el->n_groups && el->group_pattern[g] != pat) ++g;
+        if (g == el->n_groups) el->group_pattern[el->n_groups++] = pat;
+        el->group_rows[g] |= 1u << i;
+    }
     return DH_OK;
 }
 
@@ -408,9 +435,9 @@ int dh_correspondences(const int32_t* pix, const uint32_t* winner, const int32_t
     const int wpr = (W + 31) / 32;
     dim3 grid(ntiles, B);
     cudaStream_t st = as_stream(stream);
-    corr_count_kernel<<<grid, 1024, 0, st>>>(pix, winner, n_fg, cleaned_bits, H, W, wpr, stride_points, ntiles, tile_counts);
+    corr_count_kernel<<<grid, kCorrThreads, 0, st>>>(pix, winner, n_fg, cleaned_bits, H, W, wpr, stride_points, ntiles, tile_counts);
     DH_LAUNCH_CHECK();
-    corr_emit_kernel<<<grid, 1024, 0, st>>>(pix, winner, fg_index, n_fg, cleaned_bits, H, W, wpr, stride_points, ntiles,
+    corr_emit_kernel<<<grid, kCorrThreads, 0, st>>>(pix, winner, fg_index, n_fg, cleaned_bits, H, W, wpr, stride_points, ntiles,
                                             tile_counts, corr, n_corr);
     DH_LAUNCH_CHECK();
     return DH_OK;

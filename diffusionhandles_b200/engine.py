@@ -139,7 +139,7 @@ class EditEngine:
         self.cleaned_bits = torch.empty((B, H, self.wpr), dtype=i32, device=dev)
         self.tmp_bits = torch.empty((B, H, self.wpr), dtype=i32, device=dev)
         self.corr = torch.empty((B, P, 4), dtype=i64, device=dev)
-        self.corr_ws = torch.empty((B * ((P + 4095) // 4096) + 64,), dtype=i32, device=dev)
+        self.corr_ws = torch.empty((B * ((P + 1023) // 1024) + 64,), dtype=i32, device=dev)      # tile counts of dh_correspondences
         self.inv_minmax = torch.empty((B, 2), dtype=f32, device=dev)
         self.in_minmax = torch.empty((B, 2), dtype=f32, device=dev)
         self.disparity_raw = torch.empty((B, H, W), dtype=f32, device=dev)

@@ -194,7 +194,8 @@ int dh_pack_mask_bits(const float* mask, int B, int H, int W, uint32_t* bits, vo
 
 /* ---- row 6: correspondences, depth_transform.py:299-343 -------------------------------------------
  * For fg point j (raster order of the source): keep iff visible and cleaned[pix]; emits int64 (n,4)
- * rows [x_src, y_src, x_dst, y_dst] in reference order.  corr has capacity P rows per edit. */
+ * rows [x_src, y_src, x_dst, y_dst] in reference order.  corr has capacity P rows per edit.
+ * ws: int32[B * ceil(P / 1024)] tile counts. */
 int dh_correspondences(const int32_t* pix, const uint32_t* winner, const int32_t* fg_index, const int32_t* n_fg,
                        const uint32_t* cleaned_bits, int B, int H, int W, int stride_points,
                        int64_t* corr, int32_t* n_corr, void* ws, size_t ws_bytes, void* stream);
