@@ -452,6 +452,11 @@ def test_fused_guidance_loss_config3(dev, golden_pc):
         dc = [c.to(dev).requires_grad_(True) for c in curs]
         total, parts = losses.guidance_loss(dc, [o.to(dev) for o in origs], pc, fgw, bgw, bg_loss_type=lt)
         grads = torch.autograd.grad(total * 0.5, dc)            # exercises the backward scaling kernel
+        # the same evaluation without an autograd node: identical value, gradients = 2 x the scaled ones above
+        t2, parts2, g2 = losses.guidance_loss_and_grad([c.detach() for c in dc], [o.to(dev) for o in origs], pc, fgw, bgw, bg_loss_type=lt)
+        assert torch.equal(t2, total.detach()) and torch.equal(parts2, parts)
+        for ga, gb in zip(grads, g2):
+            assert torch.allclose(ga * 2.0, gb, rtol=1e-6, atol=0)
         ref_total, ref_grads = 0.0, []
         for l, (c, o_) in enumerate(zip(curs, origs)):
             vf, gf = O.foreground_loss(c.numpy(), o_.numpy(), pc_np)
