@@ -347,42 +347,62 @@ __device__ __forceinline__ WorkItem decode_item(const FusedParams& p, int item) 
     return w;
 }
 
-__device__ __forceinline__ float block_sum1(float v, float* sm) {      // over the first kLossThreads threads of the CTA
+__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kLossThreads) : "memory"); }
+
+template <int kN>
+__device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8], int gid) {
+    static_assert(kN <= 8, "red holds 8 values per warp");
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane_id() == 0) sm[warp_id()] = v;
-    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
-    float t = lane_id() < kLossWarps ? sm[lane_id()] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
-    return t;
+        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+    if (lane_id() == 0)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) red[warp_id() & (kLossWarps - 1)][i] = v[i];
+    group_sync(gid);
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = red[lane_id() & (kLossWarps - 1)][i];
+#pragma unroll
+    for (int o = kLossWarps / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
 }
 
 // Called by the compute warps of every CTA when the queue is empty; the last CTA reduces the per-channel partials in a
 // fixed order -> loss_out[0] = total, [1+2l] = fg_l, [2+2l] = bg_l, and re-arms the counters.
-__device__ void loss_finish(const FusedParams& p, float* red32, unsigned int* ticket) {
+__device__ void loss_finish(const FusedParams& p, float (*red)[8], unsigned int* ticket) {
     __threadfence();
     __syncthreads();                      // every group of the CTA is done
     if (threadIdx.x == 0) *ticket = atomicAdd(p.counters + 1, 1u);
     __syncthreads();
     if (*ticket != gridDim.x - 1 || threadIdx.x >= kLossThreads) return;
     __threadfence();
+    // the first group of the last CTA: per-channel partials -> per-layer sums, four layers (eight sums) per pass; every thread
+    // adds a fixed subset of the channels in a fixed order and the block tree is fixed, so the value is reproducible bit for bit
     float total = 0.0f;
-    for (int l = 0; l < p.n_layers; ++l) {
-        const FusedLayer& L = p.lv[l];
-        float a = 0.0f, b = 0.0f;
-        for (int c = threadIdx.x; c < L.C; c += kLossThreads) {
-            a += __ldcg(p.partial + 2 * (L.partial_begin + c));
-            b += __ldcg(p.partial + 2 * (L.partial_begin + c) + 1);
+    for (int l0 = 0; l0 < p.n_layers; l0 += 4) {
+        float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (l0 + j >= p.n_layers) break;
+            const FusedLayer& L = p.lv[l0 + j];
+            for (int c = threadIdx.x; c < L.C; c += kLossThreads) {
+                v[2 * j] += __ldcg(p.partial + 2 * (L.partial_begin + c));
+                v[2 * j + 1] += __ldcg(p.partial + 2 * (L.partial_begin + c) + 1);
+            }
         }
-        a = block_sum1(a, red32);
-        b = block_sum1(b, red32);
-        const float fg = p.fg_kind ? a / (float)p.n_fg / (float)L.C : 0.0f;
-        const float bg = p.bg_kind == 2 ? b / (float)p.n_bg_common / (float)L.C : (p.bg_kind == 1 ? b / (float)L.C : 0.0f);
-        if (threadIdx.x == 0) { p.loss_out[1 + 2 * l] = fg; p.loss_out[2 + 2 * l] = bg; }
-        if (p.fg_kind) total += L.fgw * fg;
-        if (p.bg_kind) total += L.bgw * bg;
+        block_sum<8>(v, red, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (l0 + j >= p.n_layers) break;
+            const FusedLayer& L = p.lv[l0 + j];
+            const float fg = p.fg_kind ? v[2 * j] / (float)p.n_fg / (float)L.C : 0.0f;
+            const float bg = p.bg_kind == 2 ? v[2 * j + 1] / (float)p.n_bg_common / (float)L.C : (p.bg_kind == 1 ? v[2 * j + 1] / (float)L.C : 0.0f);
+            if (threadIdx.x == 0) { p.loss_out[1 + 2 * (l0 + j)] = fg; p.loss_out[2 + 2 * (l0 + j)] = bg; }
+            if (p.fg_kind) total += L.fgw * fg;
+            if (p.bg_kind) total += L.bgw * bg;
+        }
+        group_sync(0);        // `red` is reused by the next pass
     }
     if (threadIdx.x == 0) {
         p.loss_out[0] = total;
@@ -565,27 +585,6 @@ struct FusedShared {
 
 // sum over the CTA of kN values per thread, results in every thread; fixed order (warp tree, then a tree over the warp
 // partials that every warp evaluates identically) -> deterministic.  One barrier.
-__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kLossThreads) : "memory"); }
-
-template <int kN>
-__device__ __forceinline__ void block_sum(float (&v)[kN], float (*red)[8], int gid) {
-    static_assert(kN <= 8, "red holds 8 values per warp");
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
-    if (lane_id() == 0)
-#pragma unroll
-        for (int i = 0; i < kN; ++i) red[warp_id() & (kLossWarps - 1)][i] = v[i];
-    group_sync(gid);
-#pragma unroll
-    for (int i = 0; i < kN; ++i) v[i] = red[lane_id() & (kLossWarps - 1)][i];
-#pragma unroll
-    for (int o = kLossWarps / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < kN; ++i) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
-}
-
 // One pair: acc += m |d|, cnt -= m sign(d), with t = copysign(m, d): m |d| = t d, and t is only counted when d != 0.
 // The counts are integer valued floats (|sum| < 2^24, checked on the host): every partial sum is exact, so the order of
 // the additions does not matter and the gradient stays bit-reproducible.
@@ -604,10 +603,14 @@ __device__ __forceinline__ void pair_term(float fm, float d, float& acc, float& 
 // kBinary: every background multiplicity is 0 or 1 (lists from np.nonzero) -> register bit masks for the own cells.
 // kMem: 0 = the ELL plan and the resize tables are read from global memory (through L1), 1 = the plan is in shared memory,
 // 2 = the plan and the tables of the (single) resized layer are.  A template parameter so that the accesses compile to LDS.
-template <int kG, bool kBinary, int kMem>
-__global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kernel(const __grid_constant__ FusedParams p) {
+// kGroups: groups per CTA the kernel is compiled for.  3 (80 registers) is the general build; 4 (64 registers, 1024 threads) is
+// compiled WITHOUT the resized-layer path and is used for launches whose layers all have the loss-grid resolution - which is what
+// guided_inference issues with the reference's weight schedule (its only resized layer always has weight 0 and is skipped).
+template <int kG, bool kBinary, int kMem, int kGroups>
+__global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(const __grid_constant__ FusedParams p) {
+    constexpr bool kHasSmall = kGroups < 4;
     extern __shared__ __align__(128) float fsm[];
-    __shared__ __align__(16) FusedShared shg[kMaxGroups];
+    __shared__ __align__(16) FusedShared shg[kGroups];
     const int gid = threadIdx.x / kLossThreads, tid = threadIdx.x % kLossThreads, lane = lane_id(), wid = tid >> 5;
     FusedShared& sh = shg[gid];
 #ifdef DH_LOSS_PHASE_TIMERS
@@ -826,7 +829,7 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
                 }
             }
             DH_PH(1)
-        } else {
+        } else if constexpr (kHasSmall) {
             // ------------------------------------------------------------------ planes of a layer below the loss grid
             const int h = L.h, w = L.w, hw = h * w;
             const uint32_t* const tab = kMem == 2 ? s_tab : static_cast<const uint32_t*>(L.tab);      // (kMem 2: one resized layer)
@@ -969,14 +972,14 @@ __global__ void __launch_bounds__(kLossThreads * kMaxGroups, 1) loss_fused_kerne
         unsigned int smid;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        const int slot = blockIdx.x * kMaxGroups + gid;
+        const int slot = blockIdx.x * 4 + gid;
         p.debug[4 * slot + 0] = dbg_t0; p.debug[4 * slot + 1] = t1;
         p.debug[4 * slot + 2] = dbg_items; p.debug[4 * slot + 3] = smid;
 #ifdef DH_LOSS_PHASE_TIMERS
         for (int i = 0; i < 8; ++i) p.debug[4 * 1024 + 8 * slot + i] = (unsigned long long)ph[i];
 #endif
     }
-    loss_finish(p, shg[0].red32, &shg[0].ticket);
+    loss_finish(p, shg[0].red, &shg[0].ticket);
 }
 
 __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ data, size_t n, const float* __restrict__ scale) {
@@ -1176,7 +1179,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     // per-process caches of the launch geometry queries (this entry point runs every denoising step)
     struct LaunchCache {
         int sms, max_smem;
-        size_t smem_attr_set[8];
+        size_t smem_attr_set[10];
     };
     static LaunchCache caches[64];          // zero-initialised; one entry per device (function attributes are per device)
     int dev = 0;
@@ -1217,7 +1220,9 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     fp.ell_floats = 0; fp.tab_floats = 0; fp.tab_layer = first_small >= 0 ? first_small : 0;
     const size_t ellb = sizeof(float) * ell_words, tabb = sizeof(float) * tab_words;
     const bool tab_ok = n_small_layers == 1 && tab_words > 0 && grid == 64;
-    for (int g = kMaxGroups; g >= 1 && !groups; --g) {
+    // launches without a resized layer use the 64-register build: up to four groups per SM
+    const bool flat_build = fp.n_small_items == 0 && grid == 64 && !getenv("DH_LOSS_NO_FOUR_GROUPS");
+    for (int g = flat_build ? 4 : kMaxGroups; g >= 1 && !groups; --g) {
         if (ell_words && tab_ok && ellb + tabb + g * group_bytes <= budget) { groups = g; mem = 2; }
         else if (ell_words && grid == 64 && ellb + g * group_bytes <= budget && g >= 2) { groups = g; mem = 1; }
         else if (g * group_bytes <= budget && (g >= 2 || !ell_words)) { groups = g; mem = 0; }
@@ -1232,6 +1237,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     }
     if (mem >= 1) fp.ell_floats = ell_words;
     if (mem == 2) fp.tab_floats = tab_words;
+    if (!(flat_build && mem == 1) && groups > kMaxGroups) groups = kMaxGroups;      // only the flat build runs four groups
     const int n_items = fp.n_flat_items + fp.n_small_items;
     {
         const char* e = getenv("DH_LOSS_GROUPS");       // developer knob
@@ -1241,13 +1247,15 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     const size_t smem = sizeof(float) * ((size_t)fp.ell_floats + fp.tab_floats) + groups * group_bytes;
     if (smem > budget + static_bytes) return DH_ERR_UNSUPPORTED;
     // bit 0 of plan_flags: background multiplicities are all 0/1 (lists from np.nonzero) -> register bit masks
+    const bool four = flat_build && mem == 1;      // (the flat build is instantiated with the plan in shared memory)
     // (shared-memory placement is only instantiated for the reference's 64 x 64 grid)
-    const int vi = grid == 64 ? 2 + 2 * mem + ((plan_flags & 1) ? 1 : 0) : ((plan_flags & 1) ? 1 : 0);
+    const int vi = four ? 8 + ((plan_flags & 1) ? 1 : 0) : grid == 64 ? 2 + 2 * mem + ((plan_flags & 1) ? 1 : 0) : ((plan_flags & 1) ? 1 : 0);
     void (*kernel)(const FusedParams) =
-        vi == 0 ? loss_fused_kernel<0, false, 0> : vi == 1 ? loss_fused_kernel<0, true, 0>
-        : vi == 2 ? loss_fused_kernel<64, false, 0> : vi == 3 ? loss_fused_kernel<64, true, 0>
-        : vi == 4 ? loss_fused_kernel<64, false, 1> : vi == 5 ? loss_fused_kernel<64, true, 1>
-        : vi == 6 ? loss_fused_kernel<64, false, 2> : loss_fused_kernel<64, true, 2>;
+        vi == 0 ? loss_fused_kernel<0, false, 0, 3> : vi == 1 ? loss_fused_kernel<0, true, 0, 3>
+        : vi == 2 ? loss_fused_kernel<64, false, 0, 3> : vi == 3 ? loss_fused_kernel<64, true, 0, 3>
+        : vi == 4 ? loss_fused_kernel<64, false, 1, 3> : vi == 5 ? loss_fused_kernel<64, true, 1, 3>
+        : vi == 6 ? loss_fused_kernel<64, false, 2, 3> : vi == 7 ? loss_fused_kernel<64, true, 2, 3>
+        : vi == 8 ? loss_fused_kernel<64, false, 1, 4> : loss_fused_kernel<64, true, 1, 4>;
     if (smem > lc.smem_attr_set[vi]) {
         DH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lc.smem_attr_set[vi] = smem;
