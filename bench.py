@@ -430,7 +430,7 @@ def variant_guidance_loss(dev):
                         "reference_schedule": "weights of guided_stable_diffuser.py:336-373: zero-weight layers (layer 0 always) skipped"}}
 
 
-def variant_strong_scaling(dev, rank, world, steps=5):
+def variant_strong_scaling(dev, rank, world, steps=20):
     """BASELINE config 4 as written: 256 (depth, transform) edits IN TOTAL, edit e on rank e mod N, the whole device-resident
     pipeline per edit (K1 -> K2 -> masks -> correspondences -> dense maps -> K3 on the edit's own config-2 stack) and the ONE
     NCCL gather of the per-edit result records inside the timed region.  Device time, max over ranks."""
@@ -456,9 +456,9 @@ def variant_strong_scaling(dev, rank, world, steps=5):
     levels = [torch.randn((len(mine), c, s, s), generator=gen, dtype=torch.float32, device=dev) for c, s in LEVELS]
     n_local = len(mine)
     chunk = n_local if n_local <= 64 else 64
-    # small shards are latency bound (the exact sequential centroid alone is ~0.17 ms): their chain is captured as parallel
-    # sub-chains (tools/sweep_branches.py)
-    branches = int(os.environ.get("DH_BENCH_BRANCHES", "8" if n_local <= 32 and n_local % 8 == 0 else "1"))
+    # (parallel graph branches for small shards were a gain before the geometry kernels were re-tiled and are a loss now:
+    # tools/sweep_branches.py; one chain per chunk)
+    branches = int(os.environ.get("DH_BENCH_BRANCHES", "1"))
     sweep = DeviceSweep(dev, S, LEVELS, depth, bg, mask, K, rigids, levels, chunk=chunk, use_graph=True, branches=branches)
     sweep.capture()
     # the replayed graphs must give what the plain launch chain gives (first chunk: counts and the warped stack)
