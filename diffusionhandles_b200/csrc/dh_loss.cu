@@ -1156,10 +1156,25 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     fp.partial = static_cast<float*>(ws);
     fp.counters = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + o_counter);
     fp.loss_out = loss_out;
-    {
-        const char* e = getenv("DH_LOSS_DEBUG_BUF");      // developer aid: address of a device buffer of 4 * grid u64
-        fp.debug = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
-    }
+    // developer knobs, read once per process: DH_LOSS_DEBUG_BUF (address of a device buffer for tools/k4_timeline.py),
+    // DH_LOSS_NO_FOUR_GROUPS, DH_LOSS_MEM (cap the shared-memory placement: 0, 1, 2), DH_LOSS_GROUPS (cap the groups per CTA)
+    struct Knobs {
+        unsigned long long* debug;
+        bool no_four;
+        int mem_cap, groups_cap;
+    };
+    static const Knobs knobs = [] {
+        Knobs k;
+        const char* e = getenv("DH_LOSS_DEBUG_BUF");
+        k.debug = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
+        k.no_four = getenv("DH_LOSS_NO_FOUR_GROUPS") != nullptr;
+        e = getenv("DH_LOSS_MEM");
+        k.mem_cap = e ? atoi(e) : 99;
+        e = getenv("DH_LOSS_GROUPS");
+        k.groups_cap = e && atoi(e) >= 1 ? atoi(e) : 99;
+        return k;
+    }();
+    fp.debug = knobs.debug;
     // scratch of a group: the slot arrays of a resized plane pair, overlaid with the sign counts of a flat plane
     auto up4 = [](int v) { return (v + 3) / 4 * 4; };
     ResizeLayout& lay = fp.lay;
@@ -1221,7 +1236,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     const size_t ellb = sizeof(float) * ell_words, tabb = sizeof(float) * tab_words;
     const bool tab_ok = n_small_layers == 1 && tab_words > 0 && grid == 64;
     // launches without a resized layer use the 64-register build: up to four groups per SM
-    const bool flat_build = fp.n_small_items == 0 && grid == 64 && !getenv("DH_LOSS_NO_FOUR_GROUPS");
+    const bool flat_build = fp.n_small_items == 0 && grid == 64 && !knobs.no_four;
     for (int g = flat_build ? 4 : kMaxGroups; g >= 1 && !groups; --g) {
         if (ell_words && tab_ok && ellb + tabb + g * group_bytes <= budget) { groups = g; mem = 2; }
         else if (ell_words && grid == 64 && ellb + g * group_bytes <= budget && g >= 2) { groups = g; mem = 1; }
@@ -1231,18 +1246,12 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
         if (group_bytes > budget) return DH_ERR_UNSUPPORTED;
         groups = 1;
     }
-    {
-        const char* e = getenv("DH_LOSS_MEM");       // developer knob: cap the shared-memory placement (0, 1, 2)
-        if (e && atoi(e) >= 0 && atoi(e) < mem) mem = atoi(e);
-    }
+    if (knobs.mem_cap >= 0 && knobs.mem_cap < mem) mem = knobs.mem_cap;
     if (mem >= 1) fp.ell_floats = ell_words;
     if (mem == 2) fp.tab_floats = tab_words;
     if (!(flat_build && mem == 1) && groups > kMaxGroups) groups = kMaxGroups;      // only the flat build runs four groups
     const int n_items = fp.n_flat_items + fp.n_small_items;
-    {
-        const char* e = getenv("DH_LOSS_GROUPS");       // developer knob
-        if (e && atoi(e) >= 1 && atoi(e) < groups) groups = atoi(e);
-    }
+    if (knobs.groups_cap < groups) groups = knobs.groups_cap;
     while (groups > 1 && lc.sms * (groups - 1) >= n_items) --groups;      // tiny problems: no idle groups
     const size_t smem = sizeof(float) * ((size_t)fp.ell_floats + fp.tab_floats) + groups * group_bytes;
     if (smem > budget + static_bytes) return DH_ERR_UNSUPPORTED;
