@@ -1245,3 +1245,31 @@ def test_guided_inference_reference_signature_with_injected_models(dev, K, golde
     assert torch.allclose(out, lat, rtol=1e-4, atol=1e-5), float((out - lat).abs().max())
     with pytest.raises(NotImplementedError):
         GuidedStableDiffuser(conf).guided_inference(latents0, depth, uncond, cond, acts_orig, corr)
+
+
+def test_identity_prewarp_matches_the_reference_gather(dev, golden_pc, tmp_path):
+    """the input-image identity (.npz layout of test/test_diffusion_handles.py:85-114) loaded to the device and
+    all its timesteps pre-warped through an edit's correspondences by one K3 launch == the gather the reference's losses perform
+    (feat_map[:, y_src, x_src], losses.py:46-47, :80) scattered to the destination cells."""
+    from diffusionhandles_b200.identity import InputImageIdentity, load_identity, save_identity
+    meta, g = golden_pc
+    corr = g["cfg1/corr"].astype(np.int64)
+    gen = torch.Generator().manual_seed(1)
+    T = 5
+    ident = InputImageIdentity(null_text_emb=torch.randn((T, 1, 7, 8), generator=gen), init_noise=torch.randn((1, 4, 64, 64), generator=gen),
+                               activations=[torch.randn((T, c, s, s), generator=gen) for c, s in ((12, 32), (6, 64), (5, 64))],
+                               latent_image=torch.randn((1, 4, 64, 64), generator=gen))
+    path = str(tmp_path / "input_image_identity.npz")
+    save_identity(path, ident)
+    z = np.load(path)
+    assert sorted(z.files) == sorted(["null_text_emb", "init_noise", "activations1", "activations2", "activations3", "latent_image"])
+    loaded = load_identity(path, dev)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(loaded.activations, ident.activations)) and loaded.nbytes() == ident.nbytes()
+    assert torch.equal(loaded.recorded(3)[1].cpu(), ident.activations[1][3])
+    warped = loaded.prewarp(torch.from_numpy(corr), 512)
+    for a, w in zip(ident.activations, warped):
+        side = a.shape[-1]
+        m = O.dense_source_map(corr, 512, side)                     # destination cell -> source cell (first correspondence), -1 = none
+        idx = torch.from_numpy(np.where(m >= 0, m, 0).astype(np.int64))
+        ref = a.flatten(2)[:, :, idx] * torch.from_numpy(m >= 0)
+        assert torch.equal(w.cpu().flatten(2), ref)
