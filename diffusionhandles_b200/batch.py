@@ -76,6 +76,7 @@ class EditWarpPipeline:
             self.slots.append(slot)
         self.launches_per_chunk = 4 + 2 + 2 + 4 + 2 + 1 + 2 * len(self.level_shapes) + 1
         self._table = None
+        self._idx_pinned = None
 
     def h2d_bytes_per_edit(self, edits_per_scene: float = 1.0) -> float:
         """depth + bg + mask (shared by the `edits_per_scene` edits of a scene when a scene table is used) + the stack."""
@@ -110,7 +111,12 @@ class EditWarpPipeline:
                     d[:n_scenes].copy_(h, non_blocking=True)
                 self._table_ready.record(up)
             table = self._table
-            idx_all = torch.as_tensor(list(scene_index), dtype=torch.int64).pin_memory()
+            if self._idx_pinned is None or self._idx_pinned.numel() < E:       # (pinned allocations are slow: keep the buffer)
+                self._idx_pinned = torch.empty(E, dtype=torch.int64).pin_memory()
+            idx_all = self._idx_pinned[:E]
+            idx_all.copy_(torch.as_tensor(list(scene_index), dtype=torch.int64))
+            if int(idx_all.min()) < 0 or int(idx_all.max()) >= n_scenes:
+                raise IndexError(f"scene_index outside the scene table of {n_scenes} scenes")
         for ci, e0 in enumerate(range(0, E, self.chunk)):
             slot = self.slots[ci % len(self.slots)]
             e1 = e0 + self.chunk

@@ -1273,3 +1273,40 @@ def test_identity_prewarp_matches_the_reference_gather(dev, golden_pc, tmp_path)
         idx = torch.from_numpy(np.where(m >= 0, m, 0).astype(np.int64))
         ref = a.flatten(2)[:, :, idx] * torch.from_numpy(m >= 0)
         assert torch.equal(w.cpu().flatten(2), ref)
+
+
+def test_edit_warp_pipeline_scene_table_equals_per_edit_uploads(dev, K):
+    """EditWarpPipeline.run_host with a scene table + scene index (each scene crosses PCIe once) gives exactly what per-edit uploads
+    give, and both equal the oracle's correspondence counts."""
+    from diffusionhandles_b200.batch import EditWarpPipeline
+    from diffusionhandles_b200.engine import make_rigid
+    S, n_scenes, per = 128, 2, 4
+    levels_shapes = [(8, 64), (16, 32)]
+    scenes = [O.synthetic_scene(S, 70 + i) for i in range(n_scenes)]
+    scene_index = [e // per for e in range(n_scenes * per)]
+    E = len(scene_index)
+    params = [(12.0 * e - 40.0, (0.03 * e, 0.0, 0.02 * e)) for e in range(E)]
+    rigids = [make_rigid(a, [0.0, 1.0, 0.0], list(t)) for a, t in params]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    table = [pin(np.stack([s[k] for s in scenes])) for k in range(3)]
+    per_edit = [pin(np.stack([scenes[i][k] for i in scene_index])) for k in range(3)]
+    gen = torch.Generator().manual_seed(4)
+    levels_h = [torch.randn((E, c, s, s), generator=gen).pin_memory() for c, s in levels_shapes]
+    pipe = EditWarpPipeline(dev, S, levels_shapes, chunk=4, n_streams=2)
+    outs = []
+    for mode in ("table", "per_edit"):
+        outs_h = [torch.empty_like(l).pin_memory() for l in levels_h]
+        n_corr_h = torch.empty(E, dtype=torch.int32).pin_memory()
+        if mode == "table":
+            pipe.run_host(table[0], table[1], table[2], K.cpu(), rigids, levels_h, outs_h, n_corr_h, scene_index=scene_index)
+        else:
+            pipe.run_host(per_edit[0], per_edit[1], per_edit[2], K.cpu(), rigids, levels_h, outs_h, n_corr_h)
+        outs.append((outs_h, n_corr_h.clone()))
+    assert torch.equal(outs[0][1], outs[1][1]) and int(outs[0][1].sum()) > 0
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    for e in (1, 6):
+        o = O.transform_depth_pc(*scenes[scene_index[e]], K_NP, params[e][0], (0, 1, 0), f32_translation(params[e][1]), poisson=False)
+        assert int(outs[0][1][e]) == o["correspondences"].shape[0]
+    with pytest.raises(IndexError):
+        pipe.run_host(table[0], table[1], table[2], K.cpu(), rigids, levels_h, outs[0][0], outs[0][1], scene_index=[5] * E)
