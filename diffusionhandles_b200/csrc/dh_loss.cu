@@ -841,7 +841,8 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
             const uint2* const nat_ent = reinterpret_cast<const uint2*>(tab + TH.at_nat_ent);
             const float* __restrict__ two = reinterpret_cast<const float*>(static_cast<const uint32_t*>(L.tab) + TH.at_wo);   // up^T(background
             const float* __restrict__ twt = reinterpret_cast<const float*>(static_cast<const uint32_t*>(L.tab) + TH.at_wt);   // multiplicities): L1
-            const bool overflow = n_usrc > lay.cap_usrc || n_slots > lay.cap_slots;      // under-sized buffers: poison, never corrupt
+            // under-sized buffers (or a shared-memory table copy that was cut short): poison the result, never read garbage
+            const bool overflow = n_usrc > lay.cap_usrc || n_slots > lay.cap_slots || (kMem == 2 && TH.at_wo > p.tab_floats);
             if (prev_kind == 0) group_sync(gid);      // slow warps may still read the sign counts of a flat plane
             prev_kind = 1;
             if (wt_layer != l) {        // this thread's cells of up^T(bg_trans multiplicities): the same for every plane of the layer
