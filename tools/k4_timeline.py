@@ -1,4 +1,6 @@
-"""Per-CTA timeline of the fused loss kernel (start / end / items / SM) through the DH_LOSS_DEBUG_BUF developer hook."""
+"""Per-group timeline of the fused loss kernel (start / end / items / SM) through the DH_LOSS_DEBUG_BUF developer hook, and -
+with a library built by `DH_LOSS_PHASE_TIMERS=1 python -m diffusionhandles_b200.build --force` - the cycles thread 0 of every
+group spends in each phase (profiles/r02_k4_summary.md).  Rebuild without the variable afterwards: the timers cost time."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
