@@ -41,6 +41,11 @@ class dh_loss_layer(C.Structure):
                 ("w", C.c_int32), ("fg_weight", c_float), ("bg_weight", c_float), ("resize_tables", c_void_p)]
 
 
+class dh_ddim_coeffs(C.Structure):
+    _fields_ = [("guidance_scale", c_float), ("sqrt_beta_t", c_float), ("sqrt_alpha_t", c_float), ("sqrt_alpha_prev", c_float),
+                ("sqrt_beta_prev", c_float), ("divide_by_reciprocal", C.c_int32)]
+
+
 class dh_loss_plan_desc(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("box_cells", C.c_int32), ("flags", C.c_int32), ("ell_slices", C.c_int32),
                 ("ell_groups", C.c_int32), ("n_src_cells", C.c_int32)]
@@ -107,6 +112,8 @@ _SIGNATURES = {
                                  c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "dh_scale_inplace_many": (c_int, [C.POINTER(c_void_p), C.POINTER(c_size_t), c_int, c_void_p, c_void_p]),
+    "dh_latent_step": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
+    "dh_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, C.POINTER(dh_ddim_coeffs), c_void_p, c_void_p, c_size_t, c_void_p]),
     "dh_raster_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dh_rasterize_meshes": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_float,
                                     c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -27,8 +27,10 @@ PER_FILE = {
     "dh_geometry.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_splat.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "dh_raster.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
+    "dh_guided_step.cu": ["-fmad=false", "-prec-div=true"],      # the rounding sequence of the separate torch ops
 }
-SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_loss_patch.cu", "dh_poisson.cu", "dh_raster.cu"]
+SOURCES = ["dh_geometry.cu", "dh_splat.cu", "dh_masks.cu", "dh_warp.cu", "dh_loss.cu", "dh_loss_patch.cu", "dh_poisson.cu", "dh_raster.cu",
+           "dh_guided_step.cu"]
 
 
 def _nvcc() -> str:

@@ -202,12 +202,7 @@ class GuidedStableDiffuser:
             pc = self.process_correspondences(correspondences, img_res=depth.shape[-1], bg_erosion=self._conf("bg_erosion", 0))
             if use_depth:
                 depth = self.init_depth(depth)
-            if self.tokenizer is not None and self.text_encoder is not None:
-                ids = self.tokenizer([prompt], padding="max_length", truncation=True, max_length=self.tokenizer.model_max_length,
-                                     return_tensors="pt")
-                cond = self.text_encoder(ids.input_ids.to(self.device))[0]
-            else:                                # a pre-computed prompt embedding may be passed instead of a string
-                cond = prompt
+            cond = self._encode_prompt(prompt)
             step_params = set(inspect.signature(self.scheduler.step).parameters.keys())
             extra = {}
             if "eta" in step_params:
@@ -221,14 +216,16 @@ class GuidedStableDiffuser:
             out = self.unet(model_in, t, encoder_hidden_states=cond, cross_attention_kwargs=None, return_dict=False)
             return out[0], [out[4], out[5], out[6]]
 
+        def cfg_pair(lat, t, t_idx):
+            return self._cfg_forward(lat, t, uncond_embeddings[t_idx], cond, depth if use_depth else None)
+
         def cfg_noise(lat, t, t_idx):
-            model_in = self.scheduler.scale_model_input(torch.cat([lat] * 2), t)
-            if use_depth:
-                model_in = torch.cat([model_in, torch.cat([depth] * 2, dim=0)], dim=1)
-            emb = torch.cat([uncond_embeddings[t_idx].expand(*cond.shape), cond])
-            noise = self.unet(model_in, t, encoder_hidden_states=emb, cross_attention_kwargs=None, return_dict=False)[0]
-            n_uncond, n_text = noise.chunk(2)
+            n_uncond, n_text = cfg_pair(lat, t, t_idx)
             return n_uncond + 7.5 * (n_text - n_uncond)
+
+        # a diffusers DDIMScheduler (epsilon prediction, eta = 0, no clipping: the reference's, :31-32) is replaced by the fused
+        # CFG + DDIM update; any other scheduler object keeps its own step()
+        ddim = self._fused_ddim()
 
         steps = {'opt': [], 'post-opt': []} if save_denoising_steps else None
 
@@ -245,10 +242,93 @@ class GuidedStableDiffuser:
             guidance_max_step=self._conf("guidance_max_step", 38), guidance_schedule_type=self._conf("guidance_schedule_type", "constant"),
             bg_loss_type=self._conf("bg_loss_type", "global_avg"), fg_patch_size=self._conf("fg_patch_size", 1),
             bg_patch_size=self._conf("bg_patch_size", 1), scale_model_input=self.scheduler.scale_model_input, cfg_noise=cfg_noise,
-            on_step=on_step if steps is not None else None)
+            on_step=on_step if steps is not None else None, ddim=ddim, cfg_pair=cfg_pair if ddim is not None else None)
         with torch.no_grad():
             image = self.decode_latent_image(latents)
         return (image, steps) if save_denoising_steps else image
+
+    def _fused_ddim(self):
+        """DDIMSchedule of the injected scheduler when the fused update reproduces its step(), else None."""
+        from .guided_loop import DDIMSchedule
+        if getattr(self.scheduler, "init_noise_sigma", 1.0) != 1.0:
+            return None
+        return DDIMSchedule.from_scheduler(self.scheduler)
+
+    def _cfg_forward(self, latents, t, uncond_embedding, cond, depth):
+        """The classifier-free-guidance forward (guided_stable_diffuser.py:243-263, :452-468): the latents twice, the
+        unconditional and the prompt embedding -> (noise_uncond, noise_text)."""
+        model_in = self.scheduler.scale_model_input(torch.cat([latents] * 2), t)
+        if depth is not None:
+            model_in = torch.cat([model_in, torch.cat([depth] * 2, dim=0)], dim=1)
+        emb = torch.cat([uncond_embedding.expand(*cond.shape), cond])
+        noise = self.unet(model_in, t, encoder_hidden_states=emb, cross_attention_kwargs=None, return_dict=False)[0]
+        return noise.chunk(2)
+
+    def _encode_prompt(self, prompt):
+        if self.tokenizer is not None and self.text_encoder is not None and isinstance(prompt, str):
+            ids = self.tokenizer([prompt], padding="max_length", truncation=True, max_length=self.tokenizer.model_max_length,
+                                 return_tensors="pt")
+            return self.text_encoder(ids.input_ids.to(self.device))[0]
+        if isinstance(prompt, str):
+            raise NotImplementedError("a prompt string needs the stock tokenizer / text encoder; pass them to GuidedStableDiffuser(...) "
+                                      "or pass the prompt embedding instead of the string")
+        return prompt                            # a pre-computed prompt embedding may be passed instead of a string
+
+    def initial_inference(self, init_latents: torch.Tensor, depth: torch.Tensor, uncond_embeddings: torch.Tensor, prompt: str):
+        """guided_stable_diffuser.py:155-274, same signature: the recording pass.  Per timestep one conditional U-Net forward whose
+        three guided activations are written straight into pre-allocated device-resident (T,C,h,w) stacks (``ActivationRecorder``:
+        no per-step list + final ``torch.stack`` copy of the 1.05 GB), then the classifier-free-guidance forward and the scheduler
+        update (fused into one launch for a DDIM scheduler).  Returns (activations, latents, uncond_embeddings, init_latents).
+        ``init_latents=None`` (fresh noise from the seeded generator, :192-200) needs ``scheduler.add_noise``."""
+        from .identity import ActivationRecorder
+        from .guided_loop import cfg_ddim_step
+        import inspect
+        missing = [n for n in ("unet", "scheduler") if getattr(self, n) is None]
+        if missing:
+            raise NotImplementedError(f"initial_inference needs the stock diffusion models ({', '.join(missing)}); pass them to "
+                                      "GuidedStableDiffuser(conf, unet=..., scheduler=..., vae=..., tokenizer=..., text_encoder=...)")
+        use_depth = self._conf("use_depth", True)
+        with torch.no_grad():
+            generator = torch.manual_seed(self._conf("seed", 2773))
+            n_steps = self._conf("num_timesteps", 50)
+            self.scheduler.set_timesteps(n_steps, device=self.device)
+            timesteps, _ = self.get_timesteps(n_steps, 1.0)
+            if use_depth:
+                depth = self.init_depth(depth)
+            cond = self._encode_prompt(prompt)
+            if uncond_embeddings is None:
+                uncond_embeddings = self._encode_prompt("")[[0]]
+            if uncond_embeddings.shape[0] == 0:
+                uncond_embeddings = uncond_embeddings.expand(len(timesteps), -1, -1, -1)
+            if init_latents is None:
+                cfg = self.unet.config
+                ch = cfg.in_channels - 1 if use_depth else cfg.in_channels
+                shape = [1, ch, cfg.sample_size, cfg.sample_size]
+                noise = torch.randn(shape, generator=generator, dtype=torch.float32).to(self.device)
+                init_latents = self.scheduler.add_noise(torch.zeros(shape, device=self.device, dtype=torch.float32), noise, timesteps[0])
+            step_params = set(inspect.signature(self.scheduler.step).parameters.keys())
+            extra = {}
+            if "eta" in step_params:
+                extra["eta"] = 0.0
+            if "generator" in step_params:
+                extra["generator"] = generator
+            ddim = self._fused_ddim()
+            t_host = [int(v) for v in (timesteps.tolist() if isinstance(timesteps, torch.Tensor) else timesteps)] if ddim is not None else None
+            recorder = ActivationRecorder(len(timesteps))
+            latents = init_latents
+            for t_idx, t in enumerate(timesteps):
+                model_in = self.scheduler.scale_model_input(latents, t)
+                if use_depth:
+                    model_in = torch.cat([model_in, depth], dim=1)
+                out = self.unet(model_in, t, encoder_hidden_states=cond, cross_attention_kwargs=None, return_dict=False)
+                recorder.record(t_idx, [out[4][0], out[5][0], out[6][0]])
+                uemb = uncond_embeddings[t_idx] if uncond_embeddings.shape[0] == len(timesteps) else uncond_embeddings[0]
+                n_uncond, n_text = self._cfg_forward(latents, t, uemb, cond, depth if use_depth else None)
+                if ddim is not None:
+                    latents = cfg_ddim_step(n_uncond, n_text, latents, ddim.coefficients(t_host[t_idx], 7.5)).view(latents.shape)
+                else:
+                    latents = self.scheduler.step(n_uncond + 7.5 * (n_text - n_uncond), t, latents, **extra, return_dict=False)[0]
+        return recorder.stacks(), latents, uncond_embeddings, init_latents
 
     def decode_latent_image(self, latent_image: torch.Tensor) -> torch.Tensor:
         """guided_stable_diffuser.py:285-288 (VAE decode + the [0,1] post-processing of diffusers' VaeImageProcessor)."""

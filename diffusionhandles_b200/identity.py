@@ -49,6 +49,45 @@ class InputImageIdentity:
         return warp.warp_stacks(self.activations, maps)
 
 
+class ActivationRecorder:
+    """Recording hook of the generation pass (guided_stable_diffuser.py:207-239, :269-272): the reference appends the three guided
+    activations of every timestep to Python lists and ``torch.stack``s them at the end (the 1.05 GB exists twice at that point).
+    Here the (T,C,h,w) stacks are allocated once, on the device the first activation lives on, and ``record(t_idx, acts)`` copies
+    each (C,h,w) map into its slot on the current stream - the layout ``prewarp`` / K3 / K4 read, with no further copy."""
+
+    def __init__(self, num_timesteps: int, dtype: torch.dtype = torch.float32):
+        if num_timesteps < 1:
+            raise ValueError("num_timesteps must be positive")
+        self.num_timesteps = int(num_timesteps)
+        self.dtype = dtype
+        self._stacks: List[torch.Tensor] = []
+        self._seen = [False] * self.num_timesteps
+
+    def record(self, t_idx: int, activations) -> None:
+        """activations: the three (C,h,w) maps of timestep ``t_idx`` (a leading batch dimension of 1 is accepted)."""
+        if not 0 <= t_idx < self.num_timesteps:
+            raise IndexError(f"timestep index {t_idx} outside the {self.num_timesteps} recorded steps")
+        acts = [a[0] if a.dim() == 4 else a for a in activations]
+        if not self._stacks:
+            self._stacks = [torch.empty((self.num_timesteps, *a.shape), dtype=self.dtype, device=a.device) for a in acts]
+        if len(acts) != len(self._stacks):
+            raise ValueError(f"expected {len(self._stacks)} activation maps, got {len(acts)}")
+        for stack, a in zip(self._stacks, acts):
+            if tuple(a.shape) != tuple(stack.shape[1:]):
+                raise ValueError(f"activation shape {tuple(a.shape)} differs from the recorded {tuple(stack.shape[1:])}")
+            stack[t_idx].copy_(a.detach(), non_blocking=True)
+        self._seen[t_idx] = True
+
+    def stacks(self) -> List[torch.Tensor]:
+        """The recorded (T,C,h,w) stacks; every timestep must have been recorded."""
+        if not all(self._seen):
+            raise RuntimeError(f"timesteps {[i for i, s in enumerate(self._seen) if not s]} were never recorded")
+        return self._stacks
+
+    def identity(self, null_text_emb: torch.Tensor, init_noise: torch.Tensor, latent_image: torch.Tensor) -> "InputImageIdentity":
+        return InputImageIdentity(null_text_emb=null_text_emb, init_noise=init_noise, activations=self.stacks(), latent_image=latent_image)
+
+
 def save_identity(path: str, identity: InputImageIdentity) -> None:
     """Writes the reference's ``.npz`` layout (np.savez, uncompressed)."""
     arrays = {"null_text_emb": identity.null_text_emb, "init_noise": identity.init_noise, "latent_image": identity.latent_image}

@@ -307,6 +307,31 @@ int dh_poisson_fill_source(const float* image, const uint32_t* mask_a_bits, cons
                            const float* lap_source, int B, int H, int W, float* out, int max_iter, double rel_tol,
                            int32_t* iters_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- 8(f) rank 4: the elementwise steps of guided_inference around the U-Net (one launch each) ---------------------
+ * out = latents - grad * step_size (guided_stable_diffuser.py:434, step_size 0.1); the product is rounded to fp32 before
+ * the subtraction, like the two torch ops.  out may be latents itself (in place); a partial overlap is rejected. */
+int dh_latent_step(const float* latents, const float* grad, float step_size, float* out, size_t n, void* stream);
+/* Coefficients of one DDIM update, computed by the caller in fp32 exactly as diffusers 0.23 DDIMScheduler.step does on
+ * 0-d fp32 tensors (alphas_cumprod[t] ** 0.5, (1 - alphas_cumprod[t]) ** 0.5, the same for the previous timestep;
+ * final_alpha_cumprod when that is < 0).  divide_by_reciprocal != 0: x0 = (..) * (1.0f / sqrt_alpha_t), which is what
+ * torch's CUDA division by a host scalar computes; 0: IEEE division (torch on the CPU). */
+typedef struct dh_ddim_coeffs {
+    float guidance_scale;        /* 7.5 (guided_stable_diffuser.py:471) */
+    float sqrt_beta_t;
+    float sqrt_alpha_t;
+    float sqrt_alpha_prev;
+    float sqrt_beta_prev;
+    int32_t divide_by_reciprocal;
+} dh_ddim_coeffs;
+/* Classifier-free-guidance combine + DDIM update (epsilon prediction, eta = 0, no clipping / thresholding) in one pass:
+ *   eps = noise_uncond + guidance_scale * (noise_text - noise_uncond)          guided_stable_diffuser.py:470-471 (and :262-263)
+ *   x0  = (sample - sqrt_beta_t * eps) / sqrt_alpha_t
+ *   out = sqrt_alpha_prev * x0 + sqrt_beta_prev * eps                          guided_stable_diffuser.py:474 (and :267)
+ * every product / sum rounded to fp32 separately (no FMA).  noise_text == NULL: eps = noise_uncond (plain DDIM update).
+ * eps_out (may be NULL) receives eps.  out may be sample itself. */
+int dh_cfg_ddim_step(const float* noise_uncond, const float* noise_text, const float* sample,
+                     const dh_ddim_coeffs* coeffs_host, float* out, float* eps_out, size_t n, void* stream);
+
 /* ---- row 11 / 8(f) rank 2: hard z-buffer triangle rasteriser (mesh mode), depth_transform.py:91-195 via ------------
  * pytorch3d_renderer.py:541-941.  Semantics of pytorch3d's rasterize_meshes for faces_per_pixel = 1 (PARITY UNPINNED:
  * pytorch3d is not available).  verts (V,3) fp32 world space; faces (F,3) int32; view = X R + T; NDC = (sx X/Z, sy Y/Z).

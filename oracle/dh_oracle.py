@@ -19,6 +19,8 @@ Reference lines restated here (all under ``/root/reference/diffhandles``):
 * ``process_correspondences``         guided_stable_diffuser.py:490-584
 * losses                              losses.py:4-84
 * guidance weight schedule            guided_stable_diffuser.py:336-373, :622-665
+* latent update, CFG, DDIM update     guided_stable_diffuser.py:434, :470-474 (scheduler arithmetic: diffusers 0.23, absent:
+                                      parity unpinned, see the section header)
 
 Numerics contract (SURVEY.md finding 8): the oracle reproduces the reference *as executed under this
 image* (NumPy >= 2 promotion rules: ``float32_array * np.float64 scalar -> float64``).
@@ -734,6 +736,67 @@ def guidance_weight_schedule(fg_weight: float = 1.5, bg_weight: float = 1.25, gu
         of, ob = opt[min(it, 3)]
         return [a * b for a, b in zip(df, of)], [a * b for a, b in zip(db, ob)]
     return schedule
+
+
+# --------------------------------------------------------------------------------------------
+# the elementwise steps of guided_inference around the U-Net
+#
+# PARITY UNPINNED for the scheduler arithmetic: it lives in diffusers (pyproject.toml:30 pins 0.23.*), which is not
+# installed here and not under /root/reference.  Restated from the published algorithm (DDIM, Song et al. 2021, eq. 12, as
+# DDIMScheduler.step of diffusers 0.23 evaluates it: epsilon prediction, eta = 0, no clipping) and anchored on the
+# reference's call sites (guided_stable_diffuser.py:31-32 constructor, :262-267 and :470-474 CFG + step, :434 latent update)
+# and on the published endpoints of Stable Diffusion's scaled-linear table (alphas_cumprod[0] = 0.99915, [999] = 0.00466).
+# --------------------------------------------------------------------------------------------
+def ddim_alphas_cumprod(num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012) -> np.ndarray:
+    """``torch.cumprod(1 - torch.linspace(beta_start**0.5, beta_end**0.5, N, dtype=float32)**2, 0)`` ("scaled_linear"): the
+    products are accumulated in fp64 and rounded to fp32 per element, as torch's CPU cumprod does."""
+    root = linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps)
+    alphas = f32(1.0) - root * root
+    return np.cumprod(alphas.astype(f64)).astype(f32)
+
+
+def ddim_timesteps(num_inference_steps: int, num_train_timesteps: int = 1000, steps_offset: int = 0) -> np.ndarray:
+    """"leading" spacing: multiples of N // n, descending."""
+    ratio = num_train_timesteps // num_inference_steps
+    return (np.arange(num_inference_steps)[::-1] * ratio).astype(np.int64) + steps_offset
+
+
+def cfg_combine(noise_uncond: np.ndarray, noise_text: np.ndarray, guidance_scale: float = 7.5) -> np.ndarray:
+    """guided_stable_diffuser.py:470-471 (fp32, each op rounded)."""
+    u, t = noise_uncond.astype(f32), noise_text.astype(f32)
+    return u + f32(guidance_scale) * (t - u)
+
+
+def ddim_coefficients(timestep: int, alphas_cumprod: np.ndarray, num_inference_steps: int,
+                      final_alpha_cumprod: Optional[float] = None) -> Tuple[np.float32, np.float32, np.float32, np.float32]:
+    """(sqrt(1 - a_t), sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev)) in fp32 with correctly rounded square roots.  diffusers evaluates
+    ``a ** 0.5`` on 0-d CPU tensors, i.e. with torch's CPU sqrt, which (MKL VML here) may differ from the correctly rounded value
+    by one ulp - comparisons of the coefficients therefore allow 1 ulp."""
+    n_train = alphas_cumprod.shape[0]
+    prev = timestep - n_train // num_inference_steps
+    a_t = f32(alphas_cumprod[timestep])
+    a_prev = f32(alphas_cumprod[prev]) if prev >= 0 else f32(alphas_cumprod[0] if final_alpha_cumprod is None else final_alpha_cumprod)
+    return np.sqrt(f32(1.0) - a_t), np.sqrt(a_t), np.sqrt(a_prev), np.sqrt(f32(1.0) - a_prev)
+
+
+def ddim_step(model_output: np.ndarray, timestep: int, sample: np.ndarray, alphas_cumprod: np.ndarray, num_inference_steps: int,
+              final_alpha_cumprod: Optional[float] = None, reciprocal_division: bool = False, coefficients=None) -> np.ndarray:
+    """x_{t-1} = sqrt(a_prev) * x0 + sqrt(1 - a_prev) * eps with x0 = (x_t - sqrt(1 - a_t) * eps) / sqrt(a_t); every coefficient
+    and every elementwise op in fp32.  ``reciprocal_division``: multiply by fl32(1 / sqrt(a_t)) instead of dividing (what
+    torch's CUDA kernels do for a host-scalar divisor).  ``coefficients``: use these four fp32 values instead of
+    ``ddim_coefficients`` (to separate the elementwise arithmetic from the 1-ulp question of the square roots)."""
+    if coefficients is None:
+        coefficients = ddim_coefficients(timestep, alphas_cumprod, num_inference_steps, final_alpha_cumprod)
+    sqrt_beta_t, sqrt_alpha_t, sqrt_alpha_prev, sqrt_beta_prev = (f32(c) for c in coefficients)
+    eps, x = model_output.astype(f32), sample.astype(f32)
+    num = x - sqrt_beta_t * eps
+    x0 = num * (f32(1.0) / sqrt_alpha_t) if reciprocal_division else num / sqrt_alpha_t
+    return sqrt_alpha_prev * x0 + sqrt_beta_prev * eps
+
+
+def latent_update(latents: np.ndarray, grad: np.ndarray, step_size: float = 0.1) -> np.ndarray:
+    """guided_stable_diffuser.py:434: latents - grad * 0.1 in fp32 (0.1 rounded to fp32 first, as torch does for a Python scalar)."""
+    return latents.astype(f32) - grad.astype(f32) * f32(step_size)
 
 
 # --------------------------------------------------------------------------------------------
