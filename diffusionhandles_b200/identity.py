@@ -6,8 +6,10 @@ resident on the device, so every guidance step reads them from HBM.
 """
 from __future__ import annotations
 
+import struct
+import zipfile
 from dataclasses import dataclass
-from typing import List
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -95,21 +97,106 @@ def save_identity(path: str, identity: InputImageIdentity) -> None:
     np.savez(path, **{k: v.detach().cpu().numpy() for k, v in arrays.items()})
 
 
-def load_identity(path: str, device: torch.device) -> InputImageIdentity:
-    """Reads the reference's ``.npz`` layout and places everything on ``device`` (pinned staging, async copies)."""
-    device = torch.device(device)
+def npz_member_layout(path: str) -> Optional[Dict[str, Tuple[int, tuple, np.dtype]]]:
+    """Where the arrays of an UNCOMPRESSED ``.npz`` (np.savez: ZIP_STORED members, each a ``.npy``) lie in the file:
+    ``{name: (byte offset of the raw data, shape, dtype)}``.  None when a member is compressed, Fortran-ordered or an object
+    array - the caller then falls back to ``np.load``."""
     out = {}
-    with np.load(path) as z:
-        missing = [k for k in KEYS if k not in z.files]
-        if missing:
-            raise KeyError(f"{path} is not an input-image identity file (missing {missing})")
-        for k in KEYS:
-            host = torch.from_numpy(np.ascontiguousarray(z[k]))
-            if device.type == "cuda":
-                host = host.pin_memory()
-            out[k] = host.to(device, non_blocking=True)
+    with zipfile.ZipFile(path) as zf, open(path, "rb") as f:
+        for info in zf.infolist():
+            if not info.filename.endswith(".npy"):
+                continue
+            if info.compress_type != zipfile.ZIP_STORED:
+                return None
+            f.seek(info.header_offset)
+            local = f.read(30)                       # local file header: signature, ..., name length @26, extra length @28
+            if local[:4] != b"PK\x03\x04":
+                return None
+            name_len, extra_len = struct.unpack("<HH", local[26:30])
+            f.seek(info.header_offset + 30 + name_len + extra_len)
+            version = np.lib.format.read_magic(f)
+            if version == (1, 0):
+                shape, fortran, dtype = np.lib.format.read_array_header_1_0(f)
+            elif version == (2, 0):
+                shape, fortran, dtype = np.lib.format.read_array_header_2_0(f)
+            else:
+                return None
+            if fortran or dtype.hasobject:
+                return None
+            out[info.filename[:-4]] = (f.tell(), tuple(shape), dtype)
+    return out
+
+
+class _PinnedRing:
+    """Two pinned staging buffers; a buffer is refilled only after the device copy that read it has completed."""
+
+    def __init__(self, device: torch.device, nbytes: int):
+        self.bufs = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event() for _ in range(2)]
+        self.used = [False, False]
+        self.i = 0
+        self.device = device
+
+    def upload(self, src: np.ndarray, dst: torch.Tensor) -> None:
+        """src: contiguous 1-D uint8 view (<= buffer size) of host or memory-mapped bytes; dst: 1-D uint8 device view."""
+        k, n = self.i, src.shape[0]
+        if self.used[k]:
+            self.events[k].synchronize()
+        stage = self.bufs[k][:n]
+        np.copyto(stage.numpy(), src)                # the disk read (page cache -> pinned memory) happens here
+        dst.copy_(stage, non_blocking=True)
+        self.events[k].record(torch.cuda.current_stream(self.device))
+        self.used[k] = True
+        self.i = 1 - k
+
+
+def load_identity(path: str, device: torch.device, staging_bytes: int = 64 << 20) -> InputImageIdentity:
+    """Reads the reference's ``.npz`` layout and places everything on ``device``.  For an uncompressed file (what ``np.savez``
+    and ``save_identity`` write) the arrays are memory-mapped where they lie in the archive and streamed through two pinned
+    staging buffers of ``staging_bytes``: reading chunk i+1 from disk overlaps the host->device copy of chunk i, and the 1.05 GB
+    of stacks never exist as a pageable or pinned host copy.  Compressed archives take the ``np.load`` path."""
+    device = torch.device(device)
+    layout = npz_member_layout(path)
+    names = set(layout) if layout is not None else None
+    if names is None:
+        with np.load(path) as z:
+            names = set(z.files)
+    missing = [k for k in KEYS if k not in names]
+    if missing:
+        raise KeyError(f"{path} is not an input-image identity file (missing {missing})")
+    out = {}
+    if layout is None or device.type != "cuda":
+        with np.load(path) as z:
+            for k in KEYS:
+                host = torch.from_numpy(np.ascontiguousarray(z[k]))
+                if device.type == "cuda":
+                    host = host.pin_memory()
+                out[k] = host.to(device, non_blocking=True)
+    else:
+        if staging_bytes < 4096:
+            raise ValueError("staging_bytes must be at least 4096")
+        with torch.cuda.device(device):
+            ring = _PinnedRing(device, staging_bytes)
+            for k in KEYS:
+                offset, shape, dtype = layout[k]
+                nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+                dst = torch.empty(shape, dtype=_torch_dtype(dtype), device=device)
+                if nbytes:
+                    raw = np.memmap(path, dtype=np.uint8, mode="r", offset=offset, shape=(nbytes,))
+                    flat = dst.view(-1).view(torch.uint8)
+                    for a in range(0, nbytes, staging_bytes):
+                        b = min(a + staging_bytes, nbytes)
+                        ring.upload(raw[a:b], flat[a:b])
+                    del raw
+                out[k] = dst
     if device.type == "cuda":
         torch.cuda.current_stream(device).synchronize()
     return InputImageIdentity(null_text_emb=out["null_text_emb"], init_noise=out["init_noise"],
                               activations=[out["activations1"], out["activations2"], out["activations3"]],
                               latent_image=out["latent_image"])
+
+
+def _torch_dtype(dtype: np.dtype) -> torch.dtype:
+    if dtype.byteorder == ">":
+        raise TypeError(f"big-endian arrays ({dtype}) are not supported")
+    return torch.from_numpy(np.empty(0, dtype=dtype)).dtype

@@ -686,6 +686,21 @@ def test_identity_npz_roundtrip(dev, tmp_path):
     for a, b in zip(ident.activations, back.activations):
         assert torch.equal(a, b.cpu())
     assert [tuple(t.shape) for t in back.recorded(2)] == [(12, 32, 32), (6, 64, 64), (3, 64, 64)] and back.recorded(2)[0].is_contiguous()
+    # many small chunks through the two pinned staging buffers (ragged last chunk), and a compressed archive (np.load path)
+    small = load_identity(path, dev, staging_bytes=4096 + 512)
+    for k in ("null_text_emb", "init_noise", "latent_image"):
+        assert torch.equal(getattr(small, k).cpu(), getattr(ident, k))
+    for a, b in zip(ident.activations, small.activations):
+        assert torch.equal(a, b.cpu())
+    packed = str(tmp_path / "compressed.npz")
+    np.savez_compressed(packed, **{k: v.numpy() for k, v in (("null_text_emb", ident.null_text_emb), ("init_noise", ident.init_noise),
+                                                             ("latent_image", ident.latent_image), ("activations1", ident.activations[0]),
+                                                             ("activations2", ident.activations[1]), ("activations3", ident.activations[2]))})
+    comp = load_identity(packed, dev)
+    assert all(torch.equal(a, b.cpu()) for a, b in zip(ident.activations, comp.activations))
+    with pytest.raises(KeyError):
+        np.savez(str(tmp_path / "other.npz"), x=np.zeros(3))
+        load_identity(str(tmp_path / "other.npz"), dev)
 
 
 def test_depth_to_mesh_topology(dev, K):

@@ -142,3 +142,30 @@ def test_activation_recorder():
     ident = rec.identity(torch.zeros(T, 1, 2, 2), torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8))
     assert isinstance(ident, InputImageIdentity) and ident.recorded(2)[1].shape == shapes[1]
     assert ident.nbytes() == 4 * T * sum(c * h * w for c, h, w in shapes)
+
+
+def test_identity_npz_layout_and_cpu_load(tmp_path):
+    """The uncompressed .npz the reference's drivers write (test/test_diffusion_handles.py:88-114): the loader finds every
+    array's raw bytes inside the archive (what it memory-maps and streams to the device)."""
+    from diffusionhandles_b200.identity import KEYS, load_identity, npz_member_layout, save_identity
+    g = torch.Generator().manual_seed(2)
+    ident = InputImageIdentity(null_text_emb=torch.randn(3, 1, 7, 8, generator=g), init_noise=torch.randn(1, 4, 8, 8, generator=g),
+                               activations=[torch.randn(3, 6, 4, 4, generator=g), torch.randn(3, 5, 8, 8, generator=g),
+                                            torch.randn(3, 2, 8, 8, generator=g)], latent_image=torch.randn(1, 4, 8, 8, generator=g))
+    path = str(tmp_path / "input_image_identity.npz")
+    save_identity(path, ident)
+    layout = npz_member_layout(path)
+    assert layout is not None and sorted(layout) == sorted(KEYS)
+    with np.load(path) as z:
+        for k, (offset, shape, dtype) in layout.items():
+            assert shape == z[k].shape and dtype == z[k].dtype
+            assert np.array_equal(np.memmap(path, dtype=dtype, mode="r", offset=offset, shape=shape), z[k]), k
+    back = load_identity(path, "cpu")
+    assert all(torch.equal(a, b) for a, b in zip(back.activations, ident.activations)) and torch.equal(back.init_noise, ident.init_noise)
+    packed = str(tmp_path / "compressed.npz")
+    np.savez_compressed(packed, **{k: np.zeros(3, dtype=np.float32) for k in KEYS})
+    assert npz_member_layout(packed) is None                               # compressed members: the np.load path
+    assert load_identity(packed, "cpu").latent_image.shape == (3,)
+    np.savez(str(tmp_path / "other.npz"), x=np.zeros(3))
+    with pytest.raises(KeyError):
+        load_identity(str(tmp_path / "other.npz"), "cpu")
