@@ -430,6 +430,53 @@ def variant_guidance_loss(dev):
                         "reference_schedule": "weights of guided_stable_diffuser.py:336-373: zero-weight layers (layer 0 always) skipped"}}
 
 
+def variant_guided_step(dev):
+    """the elementwise steps around the U-Net on SD2-depth latents (1,4,64,64) - the eager torch ops of
+    guided_stable_diffuser.py:434 and :470-474 (DDIMScheduler.step) against the one-launch kernels.  Wall clock of 200
+    back-to-back steps (launch bound: that is the cost the fusion removes) and device time of the same steps replayed from a
+    CUDA graph."""
+    from diffusionhandles_b200.guided_loop import DDIMSchedule, cfg_ddim_step, latent_step
+    g = torch.Generator(device=dev).manual_seed(5)
+    lat, grad, nu, nt = (torch.randn((1, 4, 64, 64), generator=g, device=dev) for _ in range(4))
+    sched = DDIMSchedule()
+    sched.set_timesteps(50)
+    t = 500
+    a_t, a_p = sched.alphas_cumprod[t], sched.alphas_cumprod[t - 20]
+    co = sched.coefficients(t)
+
+    def eager():
+        x = lat - grad * 0.1
+        eps = nu + 7.5 * (nt - nu)
+        x0 = (x - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+        return a_p ** 0.5 * x0 + (1 - a_p - 0.0 ** 2) ** 0.5 * eps
+
+    def fused():
+        return cfg_ddim_step(nu, nt, latent_step(lat, grad, 0.1), co)
+    same = bool(torch.equal(eager(), fused()))
+    out = {}
+    for name, fn in (("eager", eager), ("fused", fused)):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            fn()
+        torch.cuda.synchronize(dev)
+        out[f"{name}_wall_us"] = (time.perf_counter() - t0) / 200 * 1e6
+        gr, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()
+            side.synchronize()
+            with torch.cuda.graph(gr, stream=side):
+                for _ in range(50):
+                    fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        out[f"{name}_device_us"] = _median_ms(gr.replay, dev, n=10, warm=2) / 50 * 1e3
+    return {"guided_step": {**out, "bit_identical_to_eager": same, "launches": {"eager": 11, "fused": 2},
+                            "what": "latents - 0.1 grad, CFG 7.5 combine and the DDIM update (eta 0) on (1,4,64,64) fp32 latents, per denoising step"}}
+
+
 def variant_strong_scaling(dev, rank, world, steps=20):
     """BASELINE config 4 as written: 256 (depth, transform) edits IN TOTAL, edit e on rank e mod N, the whole device-resident
     pipeline per edit (K1 -> K2 -> masks -> correspondences -> dense maps -> K3 on the edit's own config-2 stack) and the ONE
@@ -700,6 +747,10 @@ def run_ours(args):
             variants.update(variant_guidance_loss(dev))
             variants.update(variant_single_edits(dev, with_cpu=True))
             variants.update(variant_set_foreground(dev))
+            try:
+                variants.update(variant_guided_step(dev))
+            except Exception as exc:                   # noqa: BLE001 - a side measurement must not cost the headline line
+                variants["guided_step"] = {"error": repr(exc)}
         torch.cuda.empty_cache()
 
     line = None
