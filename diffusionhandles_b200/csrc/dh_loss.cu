@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
     constexpr bool kHasSmall = kGroups < 4;
     extern __shared__ __align__(128) float fsm[];
     __shared__ __align__(16) FusedShared shg[kGroups];
+    __shared__ __align__(8) uint64_t plan_bar;       // mbarrier: the plan copy (kMem >= 1)
     const int gid = threadIdx.x / kLossThreads, tid = threadIdx.x % kLossThreads, lane = lane_id(), wid = tid >> 5;
     FusedShared& sh = shg[gid];
 #ifdef DH_LOSS_PHASE_TIMERS
@@ -640,10 +641,14 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
         tma_bulk_g2s(st_cur, L.cur + off, bytes, &sh.full);
         tma_bulk_g2s(st_org, L.orig + off, bytes, &sh.full);
     };
+    // The first item of every group is static (item b + gridDim.x * g for group g of CTA b: the longest items are spread over
+    // the SMs first), so its planes are on their way before anything else happens; later items are drawn from the queue.
+    const int n_groups_total = (int)(gridDim.x * (blockDim.x / kLossThreads));
     if (tid == 0) {
         mbar_init(&sh.full, 1);
+        if (kMem && threadIdx.x == 0) mbar_init(&plan_bar, 1);
         mbar_fence_init();
-        stage_item((int)atomicAdd(p.counters, 1u));
+        stage_item((int)(blockIdx.x + gridDim.x * gid));
     }
 
     const int G = kG ? kG : p.G, GG = G * G;
@@ -652,15 +657,15 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
     const int n_rounds = (n_slices + kLossWarps - 1) / kLossWarps;
     // the sliced-ELL plan: one copy in shared memory for all groups (kMem >= 1), else read through L1
     const uint32_t* const s_words = reinterpret_cast<const uint32_t*>(fsm);
-    if (kMem) {
-        const int n_groups32 = p.fg_kind ? p.ell_ent_cap : 0;       // (the caller's ell_groups * 32)
-        int32_t* s_off = reinterpret_cast<int32_t*>(fsm);
-        uint32_t* s_desc = reinterpret_cast<uint32_t*>(fsm) + p.ell_desc_at;
-        uint32_t* s_ent = reinterpret_cast<uint32_t*>(fsm) + p.ell_ent_at;
-        for (int i = threadIdx.x; i <= n_slices; i += blockDim.x) s_off[i] = pv.ell_off[i];
-        for (int i = threadIdx.x; i < n_slices * 32; i += blockDim.x) s_desc[i] = pv.row_desc[i];
-        for (int i = threadIdx.x; i < n_groups32 / 4; i += blockDim.x)
-            reinterpret_cast<uint4*>(s_ent)[i] = reinterpret_cast<const uint4*>(pv.ent)[i];
+    if (kMem && threadIdx.x == 0) {
+        // three TMA bulk copies (one L2 round trip, no thread waits on a load): slice offsets (padded to 16 bytes in the plan),
+        // row descriptors and entries; sizes and shared-memory offsets are the caller's (multiples of 16 bytes by construction)
+        uint32_t* const s_w = reinterpret_cast<uint32_t*>(fsm);
+        const uint32_t b_off = (uint32_t)p.ell_desc_at * 4u, b_desc = (uint32_t)n_slices * 128u, b_ent = (uint32_t)p.ell_ent_cap * 4u;
+        mbar_arrive_expect_tx(&plan_bar, b_off + b_desc + b_ent);
+        tma_bulk_g2s(s_w, pv.ell_off, b_off, &plan_bar);
+        tma_bulk_g2s(s_w + p.ell_desc_at, pv.row_desc, b_desc, &plan_bar);
+        tma_bulk_g2s(s_w + p.ell_ent_at, pv.ent, b_ent, &plan_bar);
     }
     auto ell_off_of = [&](int sl) -> int { return kMem ? (int)s_words[sl] : __ldg(pv.ell_off + sl); };
     auto row_desc_of = [&](int i) -> uint32_t { return kMem ? s_words[p.ell_desc_at + i] : __ldg(pv.row_desc + i); };
@@ -703,6 +708,7 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
             reinterpret_cast<uint4*>(fsm + p.ell_floats)[i] = reinterpret_cast<const uint4*>(g_tab)[i];
     }
     __syncthreads();
+    if (kMem) mbar_wait(&plan_bar, 0);          // the shared-memory copy of the plan has landed
 
     int prev_kind = -1;          // 0 = flat, 1 = resized: kind of this group's previous item (they share the scratch area)
     int wt_layer = -1;
@@ -719,7 +725,7 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
 #endif
     for (;;) {
         int next_item = 0;
-        if (tid == 0) next_item = (int)atomicAdd(p.counters, 1u);     // (its latency hides behind this item's work)
+        if (tid == 0) next_item = n_groups_total + (int)atomicAdd(p.counters, 1u);     // (its latency hides behind this item's work)
         mbar_wait(&sh.full, phase);
         DH_PH(0)
         phase ^= 1;
@@ -1209,7 +1215,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     // shared memory: [one copy of the sliced-ELL plan][per group: stage + scratch]; as many groups (<= 3) as fit, the plan copy
     // is dropped (entries then come through L1) before the group count goes below two
     const size_t group_bytes = sizeof(float) * ((size_t)kStageFloats + fp.scratch_floats);
-    const size_t static_bytes = 2048;       // FusedShared x kMaxGroups and the driver's reservation, rounded up
+    const size_t static_bytes = 2304;       // FusedShared x kMaxGroups and the driver's reservation, rounded up
     const size_t budget = (size_t)lc.max_smem > static_bytes ? (size_t)lc.max_smem - static_bytes : 0;
     int ell_words = 0;
     if (fg_kind && ell_slices > 0 && ell_groups > 0) {
@@ -1238,7 +1244,7 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     const bool tab_ok = n_small_layers == 1 && tab_words > 0 && grid == 64;
     // launches without a resized layer use the 64-register build: up to four groups per SM
     const bool flat_build = fp.n_small_items == 0 && grid == 64 && !knobs.no_four;
-    for (int g = flat_build ? 4 : kMaxGroups; g >= 1 && !groups; --g) {
+    for (int g = std::min(flat_build ? 4 : kMaxGroups, knobs.groups_cap); g >= 1 && !groups; --g) {
         if (ell_words && tab_ok && ellb + tabb + g * group_bytes <= budget) { groups = g; mem = 2; }
         else if (ell_words && grid == 64 && ellb + g * group_bytes <= budget && g >= 2) { groups = g; mem = 1; }
         else if (g * group_bytes <= budget && (g >= 2 || !ell_words)) { groups = g; mem = 0; }
@@ -1261,10 +1267,10 @@ int dh_guidance_loss(const dh_loss_layer* layers_host, int n_layers, int grid, c
     // (shared-memory placement is only instantiated for the reference's 64 x 64 grid)
     const int vi = four ? 8 + ((plan_flags & 1) ? 1 : 0) : grid == 64 ? 2 + 2 * mem + ((plan_flags & 1) ? 1 : 0) : ((plan_flags & 1) ? 1 : 0);
     void (*kernel)(const FusedParams) =
-        vi == 0 ? loss_fused_kernel<0, false, 0, 3> : vi == 1 ? loss_fused_kernel<0, true, 0, 3>
-        : vi == 2 ? loss_fused_kernel<64, false, 0, 3> : vi == 3 ? loss_fused_kernel<64, true, 0, 3>
-        : vi == 4 ? loss_fused_kernel<64, false, 1, 3> : vi == 5 ? loss_fused_kernel<64, true, 1, 3>
-        : vi == 6 ? loss_fused_kernel<64, false, 2, 3> : vi == 7 ? loss_fused_kernel<64, true, 2, 3>
+        vi == 0 ? loss_fused_kernel<0, false, 0, kMaxGroups> : vi == 1 ? loss_fused_kernel<0, true, 0, kMaxGroups>
+        : vi == 2 ? loss_fused_kernel<64, false, 0, kMaxGroups> : vi == 3 ? loss_fused_kernel<64, true, 0, kMaxGroups>
+        : vi == 4 ? loss_fused_kernel<64, false, 1, kMaxGroups> : vi == 5 ? loss_fused_kernel<64, true, 1, kMaxGroups>
+        : vi == 6 ? loss_fused_kernel<64, false, 2, kMaxGroups> : vi == 7 ? loss_fused_kernel<64, true, 2, kMaxGroups>
         : vi == 8 ? loss_fused_kernel<64, false, 1, 4> : loss_fused_kernel<64, true, 1, 4>;
     if (smem > lc.smem_attr_set[vi]) {
         DH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
