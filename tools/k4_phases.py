@@ -1,5 +1,8 @@
-"""Per-phase cycles of the fused loss kernel for a list of layer shapes (needs a library built with -DDH_LOSS_PHASE_TIMERS;
-point DH_B200_LIB at it).  usage: python tools/k4_phases.py 4x32 [1280x32 ...] / all"""
+"""Per-phase cycles of thread 0 of every group of the fused loss kernel, for a list of layer shapes - e.g. ONE resized item alone
+(4x32) against the full layer (1280x32): what an item costs in isolation and under load (profiles/r02_k4_summary.md).
+Needs a library built with the timers: `DH_LOSS_PHASE_TIMERS=1 python -m diffusionhandles_b200.build --force` (rebuild without
+the variable afterwards), or a side build pointed at by DH_B200_LIB.
+usage: python tools/k4_phases.py 4x32 1280x32 4x64 960x64 all"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
