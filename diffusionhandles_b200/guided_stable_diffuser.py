@@ -172,6 +172,27 @@ class GuidedStableDiffuser:
         hi = torch.amax(depth, dim=[1, 2, 3], keepdim=True)
         return 2.0 * (depth - lo) / (hi - lo) - 1.0
 
+    def get_image_shape(self):
+        """guided_stable_diffuser.py:82-85: feature shape times the VAE's down-scaling factor."""
+        h, w = self.get_feature_shape()[:2]
+        f = 2 ** (len(self.vae.config.block_out_channels) - 1) if self.vae is not None else 8
+        return (h * f, w * f, 3)
+
+    def prepare_extra_step_kwargs(self, generator, eta):
+        """guided_stable_diffuser.py:595-610: ``eta`` / ``generator`` only for schedulers whose ``step`` accepts them."""
+        import inspect
+        accepted = set(inspect.signature(self.scheduler.step).parameters.keys())
+        extra = {}
+        if "eta" in accepted:
+            extra["eta"] = eta
+        if "generator" in accepted:
+            extra["generator"] = generator
+        return extra
+
+    def encode_latent_image(self, image: torch.Tensor) -> torch.Tensor:
+        """guided_stable_diffuser.py:277-283: not implemented by the reference either."""
+        raise NotImplementedError
+
     def get_timesteps(self, num_inference_steps, strength):
         """guided_stable_diffuser.py:586-593."""
         init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
@@ -185,7 +206,6 @@ class GuidedStableDiffuser:
         the latents driven by sum_l fgw[l] L_fg,l + bgw[l] L_bg,l (ONE fused K4 launch per evaluation, :415-434), then the
         classifier-free-guidance forward (scale 7.5, :452-470) and the scheduler step; finally the VAE decode.  Needs the
         injected diffusion models; without them this raises NotImplementedError (they are outside this build)."""
-        import inspect
         from .guided_loop import guided_denoise
         missing = [n for n in ("unet", "scheduler") if getattr(self, n) is None]
         if missing:
@@ -203,12 +223,7 @@ class GuidedStableDiffuser:
             if use_depth:
                 depth = self.init_depth(depth)
             cond = self._encode_prompt(prompt)
-            step_params = set(inspect.signature(self.scheduler.step).parameters.keys())
-            extra = {}
-            if "eta" in step_params:
-                extra["eta"] = 0.0
-            if "generator" in step_params:
-                extra["generator"] = generator
+            extra = self.prepare_extra_step_kwargs(generator, 0.0)
 
         def unet_fn(model_in, t):
             if use_depth:
@@ -285,7 +300,6 @@ class GuidedStableDiffuser:
         ``init_latents=None`` (fresh noise from the seeded generator, :192-200) needs ``scheduler.add_noise``."""
         from .identity import ActivationRecorder
         from .guided_loop import cfg_ddim_step
-        import inspect
         missing = [n for n in ("unet", "scheduler") if getattr(self, n) is None]
         if missing:
             raise NotImplementedError(f"initial_inference needs the stock diffusion models ({', '.join(missing)}); pass them to "
@@ -309,12 +323,7 @@ class GuidedStableDiffuser:
                 shape = [1, ch, cfg.sample_size, cfg.sample_size]
                 noise = torch.randn(shape, generator=generator, dtype=torch.float32).to(self.device)
                 init_latents = self.scheduler.add_noise(torch.zeros(shape, device=self.device, dtype=torch.float32), noise, timesteps[0])
-            step_params = set(inspect.signature(self.scheduler.step).parameters.keys())
-            extra = {}
-            if "eta" in step_params:
-                extra["eta"] = 0.0
-            if "generator" in step_params:
-                extra["generator"] = generator
+            extra = self.prepare_extra_step_kwargs(generator, 0.0)
             ddim = self._fused_ddim()
             t_host = [int(v) for v in (timesteps.tolist() if isinstance(timesteps, torch.Tensor) else timesteps)] if ddim is not None else None
             recorder = ActivationRecorder(len(timesteps))
