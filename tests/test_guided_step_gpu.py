@@ -211,3 +211,73 @@ def test_initial_inference_records_the_stacks(dev):
     from diffusionhandles_b200.guided_stable_diffuser import GuidedStableDiffuser
     with pytest.raises(NotImplementedError):
         GuidedStableDiffuser(conf).initial_inference(latents0, depth, uncond, cond)
+
+
+def test_whole_edit_through_the_facade(dev, golden_pc, tmp_path):
+    """The reference's driver sequence (test/test_diffusion_handles.py:85-200) through the top-level API with tiny stand-in models:
+    generate_input_image (recording pass) -> identity .npz round trip -> set_foreground -> transform_foreground (geometry kernels,
+    then guided_inference with the fused loss / latent / CFG + DDIM launches).  The correspondences that reach the diffuser are the
+    reference's (golden), the edited latents equal the loop written with torch gathers."""
+    import torch.nn.functional as F
+    from diffusionhandles_b200 import DiffusionHandles
+    from diffusionhandles_b200.guided_stable_diffuser import make_guidance_weight_schedule
+    from diffusionhandles_b200.identity import load_identity, save_identity
+    meta, g = golden_pc
+    m = meta["cfg1"]
+    T = 3
+    conf, unet, gsd, gen, latents0, _, cond, uncond = _setup(dev, T)
+    conf.save_denoising_steps = False
+    dh = DiffusionHandles(SimpleNamespace(guided_diffuser=conf, depth_transform_mode='pc'), diffuser=gsd).to(dev)
+    depth, bg, mask = O.synthetic_scene(**m["scene"])
+    td, tb, tm = (torch.from_numpy(a).to(dev)[None, None] for a in (depth, bg, mask))
+    # recording pass + identity file
+    null_text, init_noise, activations, latent_image = dh.generate_input_image(td, cond, null_text_emb=uncond, init_noise=latents0.clone())
+    assert [tuple(a.shape) for a in activations] == [(T, 6, 32, 32), (T, 5, 64, 64), (T, 4, 64, 64)] and torch.equal(init_noise, latents0)
+    from diffusionhandles_b200.identity import InputImageIdentity
+    path = str(tmp_path / "input_image_identity.npz")
+    save_identity(path, InputImageIdentity(null_text_emb=null_text, init_noise=init_noise, activations=activations, latent_image=latent_image))
+    back = load_identity(path, dev)
+    assert all(torch.equal(a, b) for a, b in zip(back.activations, activations))
+    # the edit
+    seen = {}
+    real = gsd.guided_inference
+
+    def spy(**kw):
+        seen["corr"] = kw["correspondences"]
+        seen["disparity"] = kw["depth"]
+        return real(**kw)
+    gsd.guided_inference = spy
+    edited, disparity = dh.transform_foreground(td, cond, tm, tb, back.null_text_emb, back.init_noise, back.activations, rot_angle=m["angle"],
+                                                rot_axis=torch.tensor(m["axis"]), translation=torch.tensor(m["translation"]))
+    assert np.array_equal(seen["corr"].numpy(), g["cfg1/corr"].astype(np.int64))            # the reference's correspondences
+    assert disparity.shape == (1, 1, 512, 512) and edited.shape == (1, 4, 64, 64)
+    # the same guided denoising written with torch gathers (losses.py:4-84) and the scheduler's own step()
+    pc = O.process_correspondences(seen["corr"].numpy(), 512, 0)
+    ix = {k: torch.from_numpy(v).to(dev) for k, v in pc.items()}
+    sched = make_guidance_weight_schedule(1.5, 1.25, 2, 'constant')
+    d64 = gsd.init_depth(seen["disparity"])
+    sch = TinyDDIM()
+    sch.set_timesteps(T, device=dev)
+    lat = latents0.clone()
+
+    def up(a):
+        return a if a.shape[-1] == 64 else F.interpolate(a[None], size=(64, 64), mode="bilinear", align_corners=False)[0]
+    for t_idx, t in enumerate(sch.timesteps):
+        for it in range(2 if t_idx < 2 else 0):
+            l_ = lat.detach().requires_grad_(True)
+            o_ = unet(torch.cat([l_, d64], dim=1), t, encoder_hidden_states=cond)
+            fgw, bgw = sched(t_idx, it)
+            loss = 0.0
+            for li, a in enumerate((o_[4], o_[5], o_[6])):
+                cur, org = up(a[0]), up(activations[li][t_idx])
+                fg = (org[:, ix["original_y"], ix["original_x"]] - cur[:, ix["transformed_y"], ix["transformed_x"]]).abs().mean(-1).mean()
+                bgl = (org[:, ix["background_y_orig"], ix["background_x_orig"]].mean(-1) -
+                       cur[:, ix["background_y_trans"], ix["background_x_trans"]].mean(-1)).abs().mean()
+                loss = loss + fgw[li] * fg + bgw[li] * bgl
+            lat = l_.detach() - 0.1 * torch.autograd.grad(loss, [l_])[0]
+        with torch.no_grad():
+            x2 = torch.cat([torch.cat([lat] * 2), torch.cat([d64] * 2, dim=0)], dim=1)
+            n = unet(x2, t, encoder_hidden_states=torch.cat([uncond[t_idx].expand(*cond.shape), cond]))[0]
+            nu, nt = n.chunk(2)
+            lat = sch.step(nu + 7.5 * (nt - nu), t, lat)[0]
+    assert torch.allclose(edited, lat, rtol=1e-4, atol=1e-4), float((edited - lat).abs().max())
