@@ -415,6 +415,24 @@ __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Table loads with an L1 eviction priority (tables in global memory, kMem < 2): the gather tables (nat_ptr / nat_ent) are walked
+// in data-dependent order by every plane pair and should stay in L1, the tap words stream through once per pair.
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_keep_u2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_keep_s32(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // snake order of the slices over the compute warps: rounds of kLossWarps slices, every other round reversed, so that the
 // descending slice widths add up to about the same per warp
 __device__ __forceinline__ int slice_of(int round, int wid) {
@@ -882,8 +900,8 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
                     return make_float2(hy * (hx * q0[i00] + lx * q0[i01]) + ly * (hx * q0[i10] + lx * q0[i11]),
                                        hy * (hx * q1[i00] + lx * q1[i01]) + ly * (hx * q1[i10] + lx * q1[i11]));
                 };
-                for (int j = tid; j < n_usrc; j += kLossThreads) uo2[j] = bilerp2(src_taps[j], po0, po1);
-                for (int j = tid; j < n_slots; j += kLossThreads) uc2[j] = bilerp2(dst_taps[j], pc0, pc1);
+                for (int j = tid; j < n_usrc; j += kLossThreads) uo2[j] = bilerp2(kMem == 2 ? src_taps[j] : ld_stream_u4(src_taps + j), po0, po1);
+                for (int j = tid; j < n_slots; j += kLossThreads) uc2[j] = bilerp2(kMem == 2 ? dst_taps[j] : ld_stream_u4(dst_taps + j), pc0, pc1);
                 float sums[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};     // per plane: foreground sum, two background sums
                 if (p.bg_kind == 1) {     // background sums at native resolution: <wo, orig>, <wt, cur>
                     for (int i = tid * 4; i < hw; i += kLossThreads * 4) {
@@ -946,12 +964,12 @@ __global__ void __launch_bounds__(kLossThreads * kGroups, 1) loss_fused_kernel(c
                     float* g0 = L.grad + (size_t)c * hw;
                     auto gather_cell = [&](int n, float wtv) {
                         float a0 = 0.0f, a1 = 0.0f;
-                        const int k1 = nat_ptr[n + 1];
-                        for (int k = nat_ptr[n]; k < k1; k += 4) {       // (lists are padded to a multiple of four)
+                        const int k1 = kMem == 2 ? nat_ptr[n + 1] : ld_keep_s32(nat_ptr + n + 1);
+                        for (int k = kMem == 2 ? nat_ptr[n] : ld_keep_s32(nat_ptr + n); k < k1; k += 4) {       // (lists are padded to a multiple of four)
                             uint2 ne[4];
                             float2 gv[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) ne[u] = nat_ent[k + u];
+                            for (int u = 0; u < 4; ++u) ne[u] = kMem == 2 ? nat_ent[k + u] : ld_keep_u2(nat_ent + k + u);
 #pragma unroll
                             for (int u = 0; u < 4; ++u) gv[u] = gs2[ne[u].x];
 #pragma unroll
