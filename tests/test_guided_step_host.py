@@ -169,3 +169,23 @@ def test_identity_npz_layout_and_cpu_load(tmp_path):
     np.savez(str(tmp_path / "other.npz"), x=np.zeros(3))
     with pytest.raises(KeyError):
         load_identity(str(tmp_path / "other.npz"), "cpu")
+
+
+def test_oracle_step_equals_the_published_ddim_update():
+    """DDIM (Song et al. 2021), eq. 12 with sigma_t = 0, rearranged: x_{t-1} = sqrt(a_prev / a_t) x_t +
+    (sqrt(1 - a_prev) - sqrt(a_prev (1 - a_t) / a_t)) eps.  The oracle's fp32 step must agree with this closed form evaluated in
+    fp64 - an anchor that does not go through the scheduler's intermediate x0 at all."""
+    a = O.ddim_alphas_cumprod().astype(np.float64)
+    rng = np.random.default_rng(3)
+    eps, x = rng.standard_normal((4, 64, 64)), rng.standard_normal((4, 64, 64))
+    for t in O.ddim_timesteps(50):
+        t = int(t)
+        a_t, a_p = a[t], (a[t - 20] if t >= 20 else a[0])
+        closed = np.sqrt(a_p / a_t) * x + (np.sqrt(1 - a_p) - np.sqrt(a_p * (1 - a_t) / a_t)) * eps
+        got = O.ddim_step(eps.astype(np.float32), t, x.astype(np.float32), O.ddim_alphas_cumprod(), 50)
+        assert np.abs(got - closed).max() <= 2e-5 * max(1.0, np.abs(closed).max()), t
+    # chaining all 50 updates with eps = 0 scales the sample by sqrt(a_final / a_980): the telescoping product of the first factors
+    y = x.astype(np.float32)
+    for t in O.ddim_timesteps(50):
+        y = O.ddim_step(np.zeros_like(y), int(t), y, O.ddim_alphas_cumprod(), 50)
+    assert np.allclose(y, np.sqrt(a[0] / a[980]) * x, rtol=1e-4, atol=1e-5)
